@@ -1,0 +1,215 @@
+"""TEST INFRASTRUCTURE ONLY -- generates tests/golden/*.npz by running the UNMODIFIED reference.
+
+Runs only in the build container (needs /root/reference).  It imports the reference package
+``mad`` through the shims of ``ref_shims.py`` from a scratch directory that holds a
+``mad -> /root/reference/mad`` symlink (``mad/eqsp/eqsp.py:16,26`` opens its tables relative
+to the cwd), runs ``MapSpace -> Detector -> Orientator -> Descriptor`` (the order of
+``mad/MaD.py:358-368``) and ``MaD._match_dsc`` (``mad/MaD.py:414-453``) on seeded synthetic
+inputs, and stores
+
+* the input grid as uint16 levels (``grid = q / 65535`` in f32 -- exact and portable),
+* SHA-256 + a few thousand sampled values of every dense intermediate
+  (``grid_list[0]``, ``map_space``, ``gauss_list``, ``grad_list``),
+* the full sparse results: keypoints, oriented (index, main, sec) triples, ``Rfinal``,
+  descriptors (or their per-row CRC32 when large), pair lists and scores.
+
+    python oracle/gen_goldens.py [tiny small pair c1]
+
+The committed fixtures pin ``oracle/mad_oracle.py`` (tests/test_oracle_golden.py).
+"""
+import hashlib
+import os
+import sys
+import time
+import zlib
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+REF = "/root/reference"
+WORK = "/tmp/mad_ref_work"
+GOLD = os.path.join(REPO, "tests", "golden")
+
+sys.path.insert(0, HERE)
+import ref_shims  # noqa: E402
+import synth  # noqa: E402
+
+
+def _enter_workdir():
+    os.makedirs(WORK, exist_ok=True)
+    link = os.path.join(WORK, "mad")
+    if not os.path.islink(link):
+        os.symlink(os.path.join(REF, "mad"), link)
+    os.chdir(WORK)
+    sys.path.insert(0, WORK)
+    ref_shims.install()
+
+
+def sha(a):
+    a = np.ascontiguousarray(a)
+    return hashlib.sha256(a.tobytes()).hexdigest()
+
+
+def sample_positions(shape, n, seed):
+    rng = np.random.default_rng(seed)
+    return np.stack([rng.integers(0, s, size=n) for s in shape[:3]], axis=1).astype(np.int32)
+
+
+def dense_record(out, key, arr, seed):
+    arr = np.ascontiguousarray(arr)
+    out[key + "_sha256"] = np.array(sha(arr))
+    out[key + "_shape"] = np.array(arr.shape, dtype=np.int64)
+    out[key + "_dtype"] = np.array(str(arr.dtype))
+    pos = sample_positions(arr.shape, 4096, seed)
+    out[key + "_pos"] = pos
+    out[key + "_val"] = arr[pos[:, 0], pos[:, 1], pos[:, 2]]
+    out[key + "_absmax"] = np.array(float(np.abs(arr).max()))
+
+
+def run_pipeline(mrc_path, patch_size=16, want_hist=False):
+    from mad.MapSpace import MapSpace
+    from mad.Detector import Detector
+    from mad.Orientator import Orientator
+    from mad.Descriptor import Descriptor
+    Orientator.step1_reject = 0   # latent AttributeError, mad/Orientator.py:133,153
+
+    t = {}
+    ms = MapSpace(mrc_path)
+    t0 = time.perf_counter(); ms.build_space(); t["build_space"] = time.perf_counter() - t0
+    t0 = time.perf_counter(); anchors = Detector().find_anchors(ms); t["find_anchors"] = time.perf_counter() - t0
+    ori = Orientator(ori_radius=patch_size)
+    t0 = time.perf_counter(); oriented = ori.assign_orientations(ms, anchors); t["assign_orientations"] = time.perf_counter() - t0
+    dsc = Descriptor(dsc_radius=patch_size)
+    t0 = time.perf_counter(); described = dsc.generate_descriptors(ms, oriented); t["generate_descriptors"] = time.perf_counter() - t0
+    return ms, anchors, described, t
+
+
+def pack_case(name, q, voxelsp, origin, ms, anchors, described, timings, full_dsc=True):
+    out = {}
+    out["input_q"] = q
+    out["voxelsp"] = np.array(voxelsp, dtype=np.float64)
+    out["origin"] = np.array(origin, dtype=np.float64)
+    out["ms_origin"] = np.array([ms.xi, ms.yi, ms.zi], dtype=np.float64)
+    out["voxelsp_list"] = np.array(ms.voxelsp_list, dtype=np.float64)
+    dense_record(out, "up_grid", ms.grid_list[0], 11)
+    for o in range(2):
+        dense_record(out, "log%d" % o, ms.map_space[o], 20 + o)
+        dense_record(out, "gauss%d" % o, ms.gauss_list[o], 30 + o)
+        g = ms.grad_list[o]
+        out["grad%d_sha256" % o] = np.array(sha(g))
+        out["grad%d_shape" % o] = np.array(g.shape, dtype=np.int64)
+        out["grad%d_dtype" % o] = np.array(str(g.dtype))
+        pos = sample_positions(g.shape, 4096, 40 + o)
+        out["grad%d_pos" % o] = pos
+        out["grad%d_val" % o] = g[pos[:, 0], pos[:, 1], pos[:, 2], :]
+    # keypoints (Detector.find_anchors output, in order)
+    out["kp_index"] = np.array([a.index for a in anchors], dtype=np.int32)
+    out["kp_oct"] = np.array([a.oct_scale for a in anchors], dtype=np.int32)
+    out["kp_coords"] = np.array([a.coords for a in anchors], dtype=np.int32).reshape(-1, 3)
+    out["kp_map_coords"] = np.array([a.map_coords for a in anchors], dtype=np.float64).reshape(-1, 3)
+    out["kp_subv_map_coords"] = np.array([a.subv_map_coords for a in anchors], dtype=np.float64).reshape(-1, 3)
+    out["kp_val"] = np.array([a.voxel_val for a in anchors], dtype=np.float32)
+    out["kp_coord_dtypes"] = np.array("%s %s" % (np.asarray(anchors[0].map_coords).dtype,
+                                                  np.asarray(anchors[0].subv_map_coords).dtype) if anchors else "")
+    # oriented + described features (in order)
+    out["of_index"] = np.array([d.index for d in described], dtype=np.int32)
+    out["of_oct"] = np.array([d.oct_scale for d in described], dtype=np.int32)
+    out["of_main"] = np.array([d.main_bin for d in described], dtype=np.int32)
+    out["of_sec"] = np.array([d.sec_bin for d in described], dtype=np.int32)
+    out["of_coords"] = np.array([d.coords for d in described], dtype=np.int32).reshape(-1, 3)
+    out["of_subv_map_coords"] = np.array([d.subv_map_coords for d in described], dtype=np.float64).reshape(-1, 3)
+    rf = np.array([d.Rfinal for d in described], dtype=np.float64).reshape(-1, 3, 3)
+    # Rfinal depends only on (main, sec): store the unique table
+    ab = out["of_main"].astype(np.int64) * 1000 + out["of_sec"]
+    uab, first = np.unique(ab, return_index=True)
+    out["rfinal_ab"] = np.stack([uab // 1000, uab % 1000], 1).astype(np.int32)
+    out["rfinal_mat"] = rf[first]
+    same = all(np.array_equal(rf[i], rf[first[np.searchsorted(uab, ab[i])]]) for i in range(len(ab)))
+    out["rfinal_depends_only_on_ab"] = np.array(bool(same))
+    dsc = np.array([d.lin_ar_subeqsp for d in described], dtype=np.int16).reshape(-1, 1024)
+    out["dsc_sha256"] = np.array(sha(dsc))
+    out["dsc_crc32"] = np.array([zlib.crc32(row.tobytes()) for row in dsc], dtype=np.uint32)
+    out["dsc_rowsum"] = dsc.sum(1).astype(np.int32)
+    if full_dsc:
+        out["dsc"] = dsc
+    out["ref_timings_s"] = np.array([timings[k] for k in ("build_space", "find_anchors",
+                                                         "assign_orientations", "generate_descriptors")])
+    path = os.path.join(GOLD, name + ".npz")
+    np.savez_compressed(path, **out)
+    print("wrote %s  K=%d D=%d  (%.1f KB)  timings=%s" % (path, len(anchors), len(described),
+                                                       os.path.getsize(path) / 1024, timings))
+    return dsc
+
+
+def density_from_atoms(coords, resolution, voxelsp, tag):
+    """The reference's own simulator (mad/PDB.py:131), then uint16 quantisation."""
+    from mad.PDB import PDB
+    pdb_path = os.path.join(WORK, tag + ".pdb")
+    synth.write_pdb(pdb_path, coords)
+    grid, xi, yi, zi = PDB(pdb_path).structure_to_density(resolution, voxelsp)
+    q = synth.quantise_u16(grid)
+    return q, (xi, yi, zi)
+
+
+def case_from_atoms(name, coords, resolution, voxelsp, full_dsc=True):
+    q, origin = density_from_atoms(coords, resolution, voxelsp, name)
+    origin = tuple(float(int(o)) for o in origin)          # int-truncated origin (MapSpace.py:108)
+    grid = synth.dequantise_u16(q)
+    mrc_path = os.path.join(WORK, name + ".mrc")
+    ref_shims.write_mrc_stub(mrc_path, grid, voxelsp, origin)
+    ms, anchors, described, t = run_pipeline(mrc_path)
+    dsc = pack_case(name, q, voxelsp, origin, ms, anchors, described, t, full_dsc=full_dsc)
+    return described, dsc
+
+
+def rigid(coords, seed, shift):
+    rng = np.random.default_rng(seed)
+    a = rng.normal(size=(3, 3))
+    qm, _ = np.linalg.qr(a)
+    if np.linalg.det(qm) < 0:
+        qm[:, 0] = -qm[:, 0]
+    c = coords.mean(0)
+    return (coords - c) @ qm.T + c + np.asarray(shift)
+
+
+def main(which):
+    _enter_workdir()
+    os.makedirs(GOLD, exist_ok=True)
+    if "tiny" in which:
+        case_from_atoms("tiny", synth.random_walk_atoms(400, 30.0, 5), 8.0, 2.0)
+    if "small" in which:
+        case_from_atoms("small", synth.random_walk_atoms(1500, 60.0, 4), 8.0, 2.0)
+    if "pair" in which:
+        # matching golden: a 2-subunit assembly map (lo) against one of its subunits (hi)
+        from mad.MaD import MaD
+        sub_a = synth.random_walk_atoms(1200, 50.0, 21)
+        sub_b = synth.random_walk_atoms(1200, 50.0, 22)
+        asm = np.concatenate([rigid(sub_a, 31, (70.0, 10.0, 5.0)), rigid(sub_b, 32, (10.0, 60.0, 40.0))])
+        hi_list, hi_dsc = case_from_atoms("pair_hi", sub_a, 8.0, 2.0)
+        lo_list, lo_dsc = case_from_atoms("pair_lo", asm, 8.0, 2.0)
+        t0 = time.perf_counter()
+        results, lo_cloud, hi_cloud = MaD()._match_dsc(lo_list, hi_list, cc_threshold=0.6)
+        dt = time.perf_counter() - t0
+        res = np.array(results, dtype=np.float64).reshape(-1, 23)
+        # re-derive the raw contraction outputs exactly as mad/MaD.py:416-424 does
+        def unit_rows(dl):
+            return np.array([d.lin_ar_subeqsp / np.linalg.norm(d.lin_ar_subeqsp)
+                             if np.linalg.norm(d.lin_ar_subeqsp) > 0 else d.lin_ar_subeqsp for d in dl])
+        preds = np.dot(unit_rows(hi_list), unit_rows(lo_list).T)
+        pairs = np.array(np.where(preds > 0.6)).T.astype(np.int32)
+        out = dict(pairs=pairs, scores=preds[pairs[:, 0], pairs[:, 1]], cc=np.array(0.6),
+                   results=res, lo_cloud=lo_cloud, hi_cloud=hi_cloud,
+                   preds_sha256=np.array(sha(preds)), preds_shape=np.array(preds.shape),
+                   topk8_idx=np.argsort(-preds, axis=1, kind="stable")[:, :8].astype(np.int32),
+                   match_time_s=np.array(dt))
+        assert np.array_equal(res[:, 0], out["scores"])
+        path = os.path.join(GOLD, "pair_match.npz")
+        np.savez_compressed(path, **out)
+        print("wrote %s  M=%d N=%d pairs=%d" % (path, preds.shape[0], preds.shape[1], len(pairs)))
+    if "c1" in which:
+        case_from_atoms("c1", synth.random_walk_atoms(9000, 85.0, 1), 4.0, 1.0, full_dsc=False)
+
+
+if __name__ == "__main__":
+    main(sys.argv[1:] or ["tiny", "small", "pair"])
