@@ -1,0 +1,184 @@
+/*
+ * mad_b200.h -- C ABI of libmad_b200.so: the B200 (sm_100a) implementation of MaD's
+ * local-feature hot path (scale-space -> detect -> orient -> describe -> match).
+ *
+ * This is the drop-in boundary.  The reference (LBM-EPFL/MaD) is pure Python
+ * with no FFI of its own; every entry point below replaces one NumPy/SciPy/scikit-image call
+ * site of the reference (cited per function, paths relative to the reference tree), and is
+ * what a ctypes stub in the reference's classes would bind.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - grids are C-contiguous float32 [x][y][z] (z fastest), as in the reference;
+ *   - gradient fields are float4 per voxel (gx, gy, gz, 0), 16-byte aligned;
+ *   - `stream` is a cudaStream_t passed as void* (0 = default stream); calls are asynchronous
+ *     on that stream unless stated; no hidden allocation: work space is supplied by the caller
+ *     (sizes from the *_workspace_bytes helpers);
+ *   - return value: 0 = MAD_OK, negative = error (mad_last_error_string() for text).
+ */
+#ifndef MAD_B200_H
+#define MAD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MAD_OK 0
+#define MAD_ERR_ARG (-1)      /* bad argument (null pointer, size out of range)              */
+#define MAD_ERR_CUDA (-2)     /* a CUDA runtime call or kernel launch failed                  */
+#define MAD_ERR_CAPACITY (-3) /* an output list did not fit the caller's buffer               */
+#define MAD_ERR_NODEVICE (-4) /* no sm_100 device / wrong architecture for a tcgen05 kernel   */
+
+#define MAD_MAX_ORI 36        /* <= 6 main x 6 secondary orientations per keypoint            */
+#define MAD_DSC_LEN 1024      /* 64 sub-blocks x 16 zones                                      */
+
+/* One detected keypoint (mad/Detector.py:30-45, mad/DensityFeature.py:35-41). */
+typedef struct MadKeypoint {
+    int32_t vox[3];   /* integer voxel after Newton moves  (DensityFeature.coords)           */
+    int32_t oct;      /* 0 = 2x-upsampled octave, 1 = base octave                            */
+    float off[3];     /* sub-voxel offset (float32 arithmetic, as NumPy 2 does it)           */
+    float val;        /* LoG value at the ORIGINAL peak voxel (mad/Detector.py:35)            */
+    int32_t peak[3];  /* original 3x3x3-maximum voxel                                         */
+    int32_t accepted; /* 1 = passed check_localize                                            */
+} MadKeypoint;
+
+/* One oriented feature = (row in the keypoint table, main zone, secondary zone).
+ * Rfinal depends only on (main, sec): see mad_orient_tables. */
+typedef struct MadOriented {
+    int32_t kp;
+    int16_t main_bin;
+    int16_t sec_bin;
+} MadOriented;
+
+/* EQSP zone table on the device: bounds[zone] = (theta_min, phi_min, theta_max, phi_max) as
+ * float64 exactly as parsed from the reference's 4-decimal tables (mad/eqsp/sphere_*.txt). */
+typedef struct MadZoneTable {
+    int32_t n_zones;          /* 112 or 16                                                    */
+    int32_t n_belts;
+    const double* bounds;     /* [n_zones][4]                                                 */
+    const int32_t* belt_first;/* [n_belts+1] first zone index of each belt                    */
+    const double* belt_phi;   /* [n_belts+1] phi bounds of the belts                          */
+} MadZoneTable;
+
+const char* mad_last_error_string(void);
+int mad_version(void);
+/* Fills (sm_count, cc_major, cc_minor) of the current device. */
+int mad_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- a1: zero padding (np.pad, mad/MapSpace.py:117-118) ---------------------------------- */
+int mad_pad3d(const float* in, int nx, int ny, int nz, int pad, float* out, void* stream);
+
+/* ---- a2: 2x not-a-knot cubic spline upsampling + Gaussian presmoothing ------------------- */
+/* (scipy.interpolate.interp1d(kind='cubic') x3 axes, mad/MapSpace.py:137-146,191-214, then
+ *  scipy.ndimage.gaussian_filter(sigma=sig_presmooth), float64 throughout, float32 result).
+ *  base: [bx][by][bz] f32;  up: [2bx-1][2by-1][2bz-1] f32.  gauss_w_host: the (2*radius+1)
+ *  float64 weights of the presmoothing kernel, centre at [radius]; radius 0 = no smoothing.
+ *  Needs every b* >= 5. */
+size_t mad_upsample_workspace_bytes(int bx, int by, int bz);
+int mad_upsample_presmooth(const float* base, int bx, int by, int bz,
+                           const double* gauss_w_host, int radius,
+                           float* up, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a3/a4: LoG response, Gaussian-smoothed grid -------------------------------------------- */
+/* map_space = max(0, -sigma^2 * gaussian_laplace(grid, sigma)), gauss = gaussian_filter(grid,
+ * sigma)  (mad/MapSpace.py:170-173,182), with SciPy's pass structure: 1-D correlations along
+ * x, y, z with `reflect` boundaries, accumulated per output in float64 (exact_f64 = 1) or in
+ * float32 (exact_f64 = 0) and stored as float32 between passes, the three second-derivative
+ * terms summed in float32 as ((x-term + y-term) + z-term).  w0 / w2: the (2*radius+1) float64
+ * weights of the order-0 / order-2 kernels (host pointers), radius <= 16. */
+size_t mad_log_gauss_workspace_bytes(int nx, int ny, int nz);
+int mad_log_gauss(const float* grid, int nx, int ny, int nz,
+                  const double* w0_host, const double* w2_host, int radius, float scale,
+                  float* log_out, float* gauss_out, void* workspace, size_t workspace_bytes,
+                  int exact_f64, void* stream);
+
+/* ---- a4: gradient field (np.gradient, mad/MapSpace.py:187) ---------------------------------- */
+/* grad4[x][y][z] = (d/dx, d/dy, d/dz, 0): central differences, one-sided at the two ends. */
+int mad_gradient(const float* gauss, int nx, int ny, int nz, float* grad4, void* stream);
+
+/* ---- a5/a6: keypoint detection + sub-voxel refinement --------------------------------------- */
+/* peak_local_max(grid, exclude_border=border, threshold_abs=threshold) + check_localize
+ * (mad/Detector.py:26-45,53-123).  Appends one MadKeypoint per 3x3x3 maximum (accepted or
+ * not) to cand[0..cap) at *count (device counter, not reset by this call).  Unordered. */
+int mad_detect(const float* log_grid, int nx, int ny, int nz, int oct, int border,
+               float threshold, MadKeypoint* cand, int cap, int* count, void* stream);
+
+/* Orders candidates canonically (octave asc, value desc, raster index of the peak asc) and
+ * keeps the accepted ones: out[0..*out_count).  n = number of candidates (host value).
+ * dims_oct = {nx0,ny0,nz0,nx1,ny1,nz1} (host pointer) for the raster index. */
+size_t mad_sort_keypoints_workspace_bytes(int n);
+int mad_sort_keypoints(const MadKeypoint* cand, int n, const int* dims_oct_host,
+                       MadKeypoint* out, int* out_count,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a7-a10: dominant orientations ----------------------------------------------------------- */
+/* Orientator.assign_orientations (mad/Orientator.py:68-110 and helpers).  For keypoint i writes
+ * n_ori[i] (0..36) and slots[i*36 + j] = main | (sec << 16) in emission order (main asc, sec asc).
+ * grad4_oct0 / grad4_oct1 with dims as in mad_sort_keypoints; r = ori_radius//2 (8 for patch 16).
+ * r1_table: float64 [n_zones][9], row-major rotation taking zone centre -> +z (identity for 0). */
+int mad_orient(const float* grad4_oct0, const float* grad4_oct1, const int* dims_oct_host,
+               const MadKeypoint* kp, int n_kp, int r, const MadZoneTable* zones112_host,
+               const double* r1_table, int lim_main, int lim_sec,
+               int32_t* n_ori, int32_t* slots, void* stream);
+
+/* Exclusive scan of n_ori + scatter: oriented[0..*out_count) in emission order. */
+size_t mad_compact_oriented_workspace_bytes(int n_kp);
+int mad_compact_oriented(const int32_t* n_ori, const int32_t* slots, int n_kp,
+                         MadOriented* oriented, int cap, int* out_count,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a11/a12: descriptors ---------------------------------------------------------------------- */
+/* Descriptor.step06_distribute_subeqsp (mad/Descriptor.py:123-202).  dsc[i][1024] int16.
+ * rf_table / rf_inv_table: float64 [rf_zones*rf_zones][9] indexed by main*rf_zones+sec: Rfinal and
+ * inv(Rfinal) (rf_zones = 112).  r = dsc_radius//2 (8 for patch 16); lattice has 2r points per axis. */
+int mad_describe(const float* grad4_oct0, const float* grad4_oct1, const int* dims_oct_host,
+                 const MadKeypoint* kp, const MadOriented* oriented, int n_oriented, int r,
+                 const MadZoneTable* zones16_host, const double* rf_table, const double* rf_inv_table,
+                 int rf_zones, int16_t* dsc, void* stream);
+
+/* ---- a15: descriptor matching (mad/MaD.py:416-424) ---------------------------------------------- */
+/* A descriptor set prepared for matching (device pointers; the struct itself lives on the host).
+ * norm2: exact integer squared L2 norms.  half: fp16 copy [rows_padded][1024] (zero rows beyond
+ * `rows`, rows_padded a multiple of 128) -- the tensor-core operand; exact because descriptor
+ * entries are integers <= 2048.  dsc is only read by the SIMT check kernel (impl = 1). */
+typedef struct MadDscSet {
+    const int16_t* dsc;   /* [rows][1024] */
+    const void* half;     /* [rows_padded][1024] fp16 */
+    const int32_t* norm2; /* [rows] */
+    int32_t rows;
+    int32_t rows_padded;
+} MadDscSet;
+
+int mad_dsc_norms(const int16_t* dsc, int rows, int32_t* norm2, void* stream);
+int mad_dsc_to_half(const int16_t* dsc, int rows, int rows_padded, void* half_out, void* stream);
+
+/* Threshold mode (the parity contract): all (i, j) with  dot(hi_i, lo_j) / sqrt(n_i n_j) > cc in
+ * float64 (integer dot and norms exact); zero rows score 0.  Two passes: COUNT fills
+ * row_count[M]; after an exclusive scan into row_offset[M] (mad_exclusive_scan_i32_to_i64), FILL
+ * writes pair_hi[..] = i, pair_lo[row_offset[i] + t] (lo ascending) and pair_score -- i.e. the row-major
+ * order of np.where(preds > cc).
+ * impl: 0 = tcgen05 tensor-core kernel (product), 1 = SIMT integer kernel (device-side check). */
+int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int32_t* row_count, int impl,
+                    void* stream);
+int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double cc, const int64_t* row_offset,
+                   int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int impl, void* stream);
+size_t mad_exclusive_scan_workspace_bytes(int n);
+int mad_exclusive_scan_i32_to_i64(const int32_t* in, int n, int64_t* out, int64_t* total,
+                                  void* workspace, size_t workspace_bytes, void* stream);
+
+/* Top-k mode (extension): per hi row the k best lo rows by (score desc, index asc);
+ * lo_index_base is added to the stored indices (sharded reference axis).  k <= 32.
+ * topk_idx[M][k] (-1 padded), topk_score[M][k] float64 (-inf padded). */
+int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, int lo_index_base,
+                   int32_t* topk_idx, double* topk_score, int impl, void* stream);
+/* Merges G per-shard top-k lists [G][M][k] into one [M][k] with the same ordering rule. */
+int mad_topk_merge(const int32_t* idx_in, const double* score_in, int G, int M, int k,
+                   int32_t* idx_out, double* score_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAD_B200_H */

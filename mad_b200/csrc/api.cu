@@ -1,0 +1,100 @@
+// C-ABI glue of libmad_b200: error text, device info, matching entry points (dispatch between
+// the tcgen05 kernel and the SIMT check kernel -- never implicit).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+#include "match_common.cuh"
+
+static thread_local char g_err[512] = "";
+
+void mad_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int mad_sm_count() {
+    static int cached = 0;
+    if (!cached) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            cached = n;
+        else
+            return 148;
+    }
+    return cached;
+}
+
+extern "C" const char* mad_last_error_string(void) { return g_err; }
+extern "C" int mad_version(void) { return 100; }
+
+extern "C" int mad_device_info(int* sm_count, int* cc_major, int* cc_minor) {
+    MAD_CHECK_ARG(sm_count && cc_major && cc_minor);
+    int dev = 0;
+    MAD_CUDA(cudaGetDevice(&dev));
+    MAD_CUDA(cudaDeviceGetAttribute(sm_count, cudaDevAttrMultiProcessorCount, dev));
+    MAD_CUDA(cudaDeviceGetAttribute(cc_major, cudaDevAttrComputeCapabilityMajor, dev));
+    MAD_CUDA(cudaDeviceGetAttribute(cc_minor, cudaDevAttrComputeCapabilityMinor, dev));
+    return MAD_OK;
+}
+
+static int check_sets(const MadDscSet* hi, const MadDscSet* lo, int impl) {
+    MAD_CHECK_ARG(hi && lo && hi->rows >= 0 && lo->rows >= 0);
+    MAD_CHECK_ARG(impl == 0 || impl == 1);
+    if (hi->rows == 0 || lo->rows == 0) return MAD_OK;
+    MAD_CHECK_ARG(hi->norm2 && lo->norm2);
+    if (impl == 1) {
+        MAD_CHECK_ARG(hi->dsc && lo->dsc);
+    } else {
+        MAD_CHECK_ARG(hi->half && lo->half);
+        MAD_CHECK_ARG(hi->rows_padded >= hi->rows && hi->rows_padded % 128 == 0);
+        MAD_CHECK_ARG(lo->rows_padded >= lo->rows && lo->rows_padded % 128 == 0);
+    }
+    return MAD_OK;
+}
+
+static int run_match(const MadDscSet* hi, const MadDscSet* lo, double cc, int mode, int32_t* row_count,
+                     const int64_t* row_offset, int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int k, int base,
+                     int32_t* topk_idx, double* topk_score, int impl, cudaStream_t st) {
+    if (impl == 1)
+        return mad_match_simt(hi->dsc, hi->rows, lo->dsc, lo->rows, hi->norm2, lo->norm2, cc, mode, row_count, row_offset,
+                              pair_hi, pair_lo, pair_score, k, base, topk_idx, topk_score, st);
+    return mad_match_tc(hi->half, hi->rows, hi->rows_padded, lo->half, lo->rows, lo->rows_padded, hi->norm2, lo->norm2, cc,
+                        mode, row_count, row_offset, pair_hi, pair_lo, pair_score, k, base, topk_idx, topk_score, st);
+}
+
+extern "C" int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int32_t* row_count, int impl,
+                               void* stream) {
+    int rc = check_sets(hi, lo, impl);
+    if (rc != MAD_OK) return rc;
+    if (hi->rows == 0) return MAD_OK;
+    MAD_CHECK_ARG(row_count);
+    if (lo->rows == 0) {
+        MAD_CUDA(cudaMemsetAsync(row_count, 0, sizeof(int32_t) * hi->rows, (cudaStream_t)stream));
+        return MAD_OK;
+    }
+    return run_match(hi, lo, cc, 0, row_count, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, impl, (cudaStream_t)stream);
+}
+
+extern "C" int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double cc, const int64_t* row_offset,
+                              int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int impl, void* stream) {
+    int rc = check_sets(hi, lo, impl);
+    if (rc != MAD_OK) return rc;
+    if (hi->rows == 0 || lo->rows == 0) return MAD_OK;
+    MAD_CHECK_ARG(row_offset && pair_hi && pair_lo && pair_score);
+    return run_match(hi, lo, cc, 1, nullptr, row_offset, pair_hi, pair_lo, pair_score, 0, 0, nullptr, nullptr, impl, (cudaStream_t)stream);
+}
+
+extern "C" int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, int lo_index_base, int32_t* topk_idx,
+                              double* topk_score, int impl, void* stream) {
+    int rc = check_sets(hi, lo, impl);
+    if (rc != MAD_OK) return rc;
+    MAD_CHECK_ARG(k >= 1 && k <= MAD_TOPK_MAX);
+    if (hi->rows == 0) return MAD_OK;
+    MAD_CHECK_ARG(topk_idx && topk_score);
+    return run_match(hi, lo, 0.0, 2, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, topk_idx, topk_score, impl,
+                     (cudaStream_t)stream);
+}

@@ -1,0 +1,123 @@
+// a11/a12: 1024-bin descriptors (Descriptor.step06_distribute_subeqsp, mad/Descriptor.py:123-202)
+// for B200 (sm_100a).
+//
+// One CTA per oriented feature.  The (2r)^3 sample lattice is rotated by inv(Rfinal) about the
+// integer keypoint voxel in float64, the gradient is fetched with SciPy's nearest rule
+// (half rounds DOWN) as one 16-byte load per sample, normalised in float32, rotated by Rfinal in
+// float64, classified into the 16 EQSP zones (highest passing index wins, unassigned -> zone 0)
+// and counted per 4x4x4 sub-block in a shared-memory histogram; the int16[1024] row is written
+// with coalesced stores.  Any sample outside the grid zeroes the whole descriptor (:140-149).
+#include "common.cuh"
+#include "eqsp_zones.cuh"
+
+namespace {
+
+struct OctDims { int n[2][3]; };
+
+__device__ __forceinline__ int nearest_idx(double p, int n) {
+    int i = (int)floor(p);
+    i = max(0, min(i, n - 2));
+    return (p - (double)i <= 0.5) ? i : i + 1;     // scipy _rgi: where(norm_dist <= .5, i, i + 1)
+}
+
+__global__ void __launch_bounds__(256)
+describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1, OctDims dims,
+                const MadKeypoint* __restrict__ kp, const MadOriented* __restrict__ oriented, int r,
+                ZoneTab T, const double* __restrict__ rf_table, const double* __restrict__ rf_inv_table,
+                int rf_zones, int16_t* __restrict__ dsc) {
+    __shared__ int cnt[MAD_DSC_LEN];
+    const int tid = threadIdx.x;
+    const MadOriented of = oriented[blockIdx.x];
+    const MadKeypoint K = kp[of.kp];
+    const int o = K.oct ? 1 : 0;
+    const float4* __restrict__ grad = o ? grad1 : grad0;
+    const int nx = dims.n[o][0], ny = dims.n[o][1], nz = dims.n[o][2];
+    const long long tab = ((long long)of.main_bin * rf_zones + of.sec_bin) * 9;
+    double Rm[9], Ri[9];
+#pragma unroll
+    for (int q = 0; q < 9; ++q) { Rm[q] = rf_table[tab + q]; Ri[q] = rf_inv_table[tab + q]; }
+    const int side = 2 * r;
+    const int total = side * side * side;
+    const int c1 = r / 2, c2 = r, c3 = (3 * r) / 2;
+    const double cx = K.vox[0], cy = K.vox[1], cz = K.vox[2];
+    const double u0 = o ? (-(double)r + 0.5) : (double)(-2 * r + 1);
+    const double du = o ? 1.0 : 2.0;
+
+    for (int q = tid; q < MAD_DSC_LEN; q += blockDim.x) cnt[q] = 0;
+
+    // pass 1: whole-patch bounds vote (RegularGridInterpolator bounds_error)
+    int bad = 0;
+    for (int sidx = tid; sidx < total; sidx += blockDim.x) {
+        const int k = sidx % side, j = (sidx / side) % side, i = sidx / (side * side);
+        const double lx = u0 + du * i, ly = u0 + du * j, lz = u0 + du * k;
+        const double px = ((lx * Ri[0] + ly * Ri[1]) + lz * Ri[2]) + cx;
+        const double py = ((lx * Ri[3] + ly * Ri[4]) + lz * Ri[5]) + cy;
+        const double pz = ((lx * Ri[6] + ly * Ri[7]) + lz * Ri[8]) + cz;
+        if (px < 0.0 || px > (double)(nx - 1) || py < 0.0 || py > (double)(ny - 1) || pz < 0.0 || pz > (double)(nz - 1)) bad = 1;
+    }
+    const int any_bad = __syncthreads_or(bad);
+    int16_t* out = dsc + (long long)blockIdx.x * MAD_DSC_LEN;
+    if (any_bad) {
+        for (int q = tid; q < MAD_DSC_LEN; q += blockDim.x) out[q] = 0;
+        return;
+    }
+
+    for (int sidx = tid; sidx < total; sidx += blockDim.x) {
+        const int k = sidx % side, j = (sidx / side) % side, i = sidx / (side * side);
+        const double lx = u0 + du * i, ly = u0 + du * j, lz = u0 + du * k;
+        const double px = ((lx * Ri[0] + ly * Ri[1]) + lz * Ri[2]) + cx;
+        const double py = ((lx * Ri[3] + ly * Ri[4]) + lz * Ri[5]) + cy;
+        const double pz = ((lx * Ri[6] + ly * Ri[7]) + lz * Ri[8]) + cz;
+        const int ix = nearest_idx(px, nx), iy = nearest_idx(py, ny), iz = nearest_idx(pz, nz);
+        float4 g = __ldg(grad + ((long long)ix * ny + iy) * nz + iz);
+        const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
+        if (m < 1e-5f) continue;                    // zone -1: never counted (:190)
+        if (m > 1e-12f) {
+            g.x = __fdiv_rn(g.x, m);
+            g.y = __fdiv_rn(g.y, m);
+            g.z = __fdiv_rn(g.z, m);
+        }
+        const double vx0 = g.x, vy0 = g.y, vz0 = g.z;
+        const double vx = (vx0 * Rm[0] + vy0 * Rm[1]) + vz0 * Rm[2];
+        const double vy = (vx0 * Rm[3] + vy0 * Rm[4]) + vz0 * Rm[5];
+        const double vz = (vx0 * Rm[6] + vy0 * Rm[7]) + vz0 * Rm[8];
+        double th = atan2(vy, vx);
+        if (th < 0.0) th += MAD_TWO_PI;
+        const double sth = th + MAD_TWO_PI;
+        const double ph = acos(fmin(1.0, fmax(-1.0, vz)));
+        int z[2];
+        const int nzn = zones_of(T, th, sth, ph, z);
+        int zone = 0;                               // unassigned directions stay in zone 0 (:173)
+        if (nzn == 1) zone = z[0];
+        else if (nzn >= 2) zone = max(z[0], z[1]);  // ascending assignment: the higher index wins
+        const int bx = (i >= c1) + (i >= c2) + (i >= c3);
+        const int by = (j >= c1) + (j >= c2) + (j >= c3);
+        const int bz = (k >= c1) + (k >= c2) + (k >= c3);
+        atomicAdd(&cnt[(16 * by + 4 * bx + bz) * T.n_zones + zone], 1);
+    }
+    __syncthreads();
+    for (int q = tid; q < MAD_DSC_LEN; q += blockDim.x) out[q] = (int16_t)cnt[q];
+}
+
+}  // namespace
+
+extern "C" int mad_describe(const float* grad4_oct0, const float* grad4_oct1, const int* dims_oct_host,
+                            const MadKeypoint* kp, const MadOriented* oriented, int n_oriented, int r,
+                            const MadZoneTable* zones_host, const double* rf_table, const double* rf_inv_table,
+                            int rf_zones, int16_t* dsc, void* stream) {
+    MAD_CHECK_ARG(dims_oct_host && zones_host && n_oriented >= 0);
+    if (n_oriented == 0) return MAD_OK;
+    MAD_CHECK_ARG(grad4_oct0 && grad4_oct1 && kp && oriented && rf_table && rf_inv_table && dsc);
+    MAD_CHECK_ARG(zones_host->n_zones * 64 == MAD_DSC_LEN);   // 64 sub-blocks x 16 zones
+    MAD_CHECK_ARG(r >= 2 && r <= 16 && rf_zones > 0);
+    OctDims d;
+    for (int o = 0; o < 2; ++o) for (int a = 0; a < 3; ++a) d.n[o][a] = dims_oct_host[3 * o + a];
+    ZoneTab T;
+    T.bounds = zones_host->bounds; T.belt_first = zones_host->belt_first; T.belt_phi = zones_host->belt_phi;
+    T.n_zones = zones_host->n_zones; T.n_belts = zones_host->n_belts;
+    describe_kernel<<<n_oriented, 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, oriented, r,
+        T, rf_table, rf_inv_table, rf_zones, dsc);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}

@@ -1,0 +1,39 @@
+// Shared pieces of the descriptor-matching kernels (mad/MaD.py:416-424).
+#pragma once
+#include <math.h>
+#include "common.cuh"
+
+#define MAD_TOPK_MAX 32
+
+// cosine similarity from the exact integer dot product and exact squared norms, in float64:
+// one sqrt and one division, both correctly rounded (IEEE) on host and device alike.
+__host__ __device__ __forceinline__ double mad_score(int dot, double n2a, double n2b) {
+    const double p = n2a * n2b;
+    return p > 0.0 ? (double)dot / sqrt(p) : 0.0;   // zero descriptors stay zero vectors (:416-417)
+}
+
+// Keeps (bs, bi)[0..k) sorted by (score descending, index ascending).
+__host__ __device__ __forceinline__ void mad_topk_insert(double* bs, int* bi, int k, double s, int id) {
+    const double ls = bs[k - 1];
+    const int li = bi[k - 1];
+    if (!(s > ls || (s == ls && (li < 0 || id < li)))) return;
+    int q = k - 1;
+    while (q > 0) {
+        const double ps = bs[q - 1];
+        const int pi = bi[q - 1];
+        if (s > ps || (s == ps && (pi < 0 || id < pi))) { bs[q] = ps; bi[q] = pi; --q; }
+        else break;
+    }
+    bs[q] = s;
+    bi[q] = id;
+}
+
+int mad_match_simt(const int16_t* hi, int M, const int16_t* lo, int N, const int32_t* hi_n2, const int32_t* lo_n2,
+                   double cc, int mode, int32_t* row_count, const int64_t* row_offset, int32_t* pair_hi,
+                   int32_t* pair_lo, double* pair_score, int k, int lo_index_base, int32_t* topk_idx,
+                   double* topk_score, cudaStream_t st);
+
+int mad_match_tc(const void* hi_half, int M, int M_pad, const void* lo_half, int N, int N_pad,
+                 const int32_t* hi_n2, const int32_t* lo_n2, double cc, int mode, int32_t* row_count,
+                 const int64_t* row_offset, int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int k,
+                 int lo_index_base, int32_t* topk_idx, double* topk_score, cudaStream_t st);

@@ -1,0 +1,260 @@
+// a7-a10: dominant orientations (Orientator.assign_orientations, mad/Orientator.py:68-110,
+// step01..step05 and process_df_gradient :116-343) for B200 (sm_100a).
+//
+// One CTA per keypoint.  The (2r+1)^3 gradient patch is gathered once (float4 per voxel, stride
+// 2 in the upsampled octave), normalised in float32 exactly as NumPy does, and kept in shared
+// memory; the spherical-mask voxels vote into a shared-memory histogram over the 112 EQSP
+// zones (float32 angles for the unrotated patch, float64 after a rotation, as in the reference).
+// Candidate selection (80 % rule, <= 6 main / <= 6 secondary) is done in the same kernel and
+// the (main, sec) pairs land in a fixed 36-slot row per keypoint: no host round trip.
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+#include "eqsp_zones.cuh"
+
+namespace {
+
+struct OctDims { int n[2][3]; };
+
+__device__ __forceinline__ int norm50(int h, int hmax) {
+    return (int)((double)h / (double)hmax * 50.0);   // np.array(h / max * 50, dtype=int32)
+}
+
+__global__ void __launch_bounds__(128)
+orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1, OctDims dims,
+              const MadKeypoint* __restrict__ kp, int r, const char4* __restrict__ mask_off, int n_mask,
+              ZoneTab T, const double* __restrict__ r1_table, int lim_main, int lim_sec,
+              int32_t* __restrict__ n_ori, int32_t* __restrict__ slots) {
+    extern __shared__ float4 pv[];     // [n_mask] normalised gradient (x, y, z, weight)
+    __shared__ int hist[128];
+    __shared__ int hn0[128];
+    __shared__ int cur[128];
+    __shared__ int s_main[8];
+    __shared__ int s_nmain, s_hmax, s_count;
+
+    const int tid = threadIdx.x;
+    const int ki = blockIdx.x;
+    const MadKeypoint K = kp[ki];
+    const int o = K.oct ? 1 : 0;
+    const float4* __restrict__ grad = o ? grad1 : grad0;
+    const int nx = dims.n[o][0], ny = dims.n[o][1], nz = dims.n[o][2];
+    const int s = o ? 1 : 2;
+    const int cx = K.vox[0], cy = K.vox[1], cz = K.vox[2];
+    // border rejection of mad/Orientator.py:129-135,149-155 (uniform over the CTA)
+    if (cx - s * r < 0 || cy - s * r < 0 || cz - s * r < 0 ||
+        cx + s * r + 1 > nx - 1 || cy + s * r + 1 > ny - 1 || cz + s * r + 1 > nz - 1) {
+        if (tid == 0) n_ori[ki] = 0;
+        return;
+    }
+    if (tid < 128) { hist[tid] = 0; }
+    if (tid == 0) { s_hmax = 0; s_count = 0; s_nmain = 0; }
+    __syncthreads();
+
+    // ---- step01 + first histogram (float32 angles against float64 bounds) ----
+    for (int i = tid; i < n_mask; i += blockDim.x) {
+        const char4 d = mask_off[i];
+        const long long idx = ((long long)(cx + s * d.x) * ny + (cy + s * d.y)) * nz + (cz + s * d.z);
+        float4 g = __ldg(grad + idx);
+        const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
+        if (m > 1e-5f) {
+            g.x = __fdiv_rn(g.x, m);
+            g.y = __fdiv_rn(g.y, m);
+            g.z = __fdiv_rn(g.z, m);
+        }
+        g.w = (m < 1e-5f) ? 0.f : 1.f;
+        pv[i] = g;
+        if (g.w != 0.f) {
+            float th = (float)atan2((double)g.y, (double)g.x);
+            if (th < 0.f) th = __fadd_rn(th, 6.2831855f);
+            const float sth = __fadd_rn(th, 6.2831855f);
+            const float zc = fminf(1.f, fmaxf(-1.f, g.z));
+            const float ph = (float)acos((double)zc);
+            int z[2];
+            const int nzn = zones_of(T, (double)th, (double)sth, (double)ph, z);
+            if (nzn > 0) atomicAdd(&hist[z[0]], 1);
+            if (nzn > 1) atomicAdd(&hist[z[1]], 1);
+        }
+    }
+    __syncthreads();
+    if (tid < T.n_zones) atomicMax(&s_hmax, hist[tid]);
+    __syncthreads();
+    const int hmax0 = s_hmax;
+    if (hmax0 == 0) {                      // no votes at all: no candidates (mad/Orientator.py:336-337,181)
+        if (tid == 0) n_ori[ki] = 0;
+        return;
+    }
+    if (tid < T.n_zones) hn0[tid] = norm50(hist[tid], hmax0);
+    __syncthreads();
+    if (tid == 0) {
+        int nm = 0;
+        for (int a = 0; a < T.n_zones; ++a)
+            if (hn0[a] > 40) { if (nm < 8) s_main[nm] = a; ++nm; }   // > max(hn)*0.8 with max(hn) == 50
+        s_nmain = nm;
+    }
+    __syncthreads();
+    const int nmain = s_nmain;
+    if (nmain > lim_main) {
+        if (tid == 0) n_ori[ki] = 0;
+        return;
+    }
+
+    for (int mi = 0; mi < nmain; ++mi) {
+        const int a = s_main[mi];
+        bool have = true;
+        if (a != 0) {
+            // ---- step03: rotate the patch so that the centre of zone a goes to +z, re-histogram (float64) ----
+            if (tid < 128) hist[tid] = 0;
+            if (tid == 0) s_hmax = 0;
+            __syncthreads();
+            const double* R = r1_table + 9 * a;
+            const double r00 = R[0], r01 = R[1], r02 = R[2], r10 = R[3], r11 = R[4], r12 = R[5], r20 = R[6], r21 = R[7], r22 = R[8];
+            for (int i = tid; i < n_mask; i += blockDim.x) {
+                const float4 g = pv[i];
+                if (g.w == 0.f) continue;
+                const double px = g.x, py = g.y, pz = g.z;
+                const double vx = fma(pz, r02, fma(py, r01, px * r00));
+                const double vy = fma(pz, r12, fma(py, r11, px * r10));
+                const double vz = fma(pz, r22, fma(py, r21, px * r20));
+                double th = atan2(vy, vx);
+                if (th < 0.0) th += MAD_TWO_PI;
+                const double sth = th + MAD_TWO_PI;
+                const double ph = acos(fmin(1.0, fmax(-1.0, vz)));
+                int z[2];
+                const int nzn = zones_of(T, th, sth, ph, z);
+                if (nzn > 0) atomicAdd(&hist[z[0]], 1);
+                if (nzn > 1) atomicAdd(&hist[z[1]], 1);
+            }
+            __syncthreads();
+            if (tid < T.n_zones) atomicMax(&s_hmax, hist[tid]);
+            __syncthreads();
+            const int hm = s_hmax;
+            if (hm == 0) have = false;
+            else if (tid < T.n_zones) cur[tid] = norm50(hist[tid], hm);
+        } else {
+            if (tid < T.n_zones) cur[tid] = hn0[tid];
+        }
+        __syncthreads();
+        // ---- step04/05: secondary zones among 1..n_zones-2 ----
+        if (tid == 0 && have) {
+            int qmax = 0;
+            for (int b = 1; b < T.n_zones - 1; ++b) qmax = max(qmax, cur[b]);
+            if (qmax > 0) {
+                int ns = 0;
+                int sec[8];
+                for (int b = 1; b < T.n_zones - 1; ++b)
+                    if (norm50(cur[b], qmax) > 40) { if (ns < 8) sec[ns] = b; ++ns; }
+                if (ns <= lim_sec) {
+                    int c = s_count;
+                    for (int q = 0; q < ns && c < MAD_MAX_ORI; ++q) slots[(long long)ki * MAD_MAX_ORI + c++] = a | (sec[q] << 16);
+                    s_count = c;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (tid == 0) n_ori[ki] = s_count;
+}
+
+__global__ void compact_oriented_kernel(const int32_t* __restrict__ n_ori, const int32_t* __restrict__ slots,
+                                        const int* __restrict__ pos, int n_kp, MadOriented* __restrict__ out,
+                                        int cap, int* __restrict__ out_count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_kp) return;
+    const int n = n_ori[i], p = pos[i];
+    for (int q = 0; q < n; ++q) {
+        if (p + q < cap) {
+            const int v = slots[(long long)i * MAD_MAX_ORI + q];
+            MadOriented of;
+            of.kp = i;
+            of.main_bin = (int16_t)(v & 0xFFFF);
+            of.sec_bin = (int16_t)(v >> 16);
+            out[p + q] = of;
+        }
+    }
+    if (i == n_kp - 1) *out_count = p + n;
+}
+
+}  // namespace
+
+// Host-side cache of the spherical-mask offsets (mad/Orientator.py:38-47), one per radius.
+static char4* g_mask_dev[32] = {nullptr};
+static int g_mask_count[32] = {0};
+
+static int ensure_mask(int r, const char4** dev, int* count) {
+    if (r < 1 || r >= 32) return MAD_ERR_ARG;
+    if (!g_mask_dev[r]) {
+        const double lim = r * 1.05;
+        const int side = 2 * r + 1;
+        char4* host = (char4*)malloc(sizeof(char4) * side * side * side);
+        int n = 0;
+        for (int dx = -r; dx <= r; ++dx)
+            for (int dy = -r; dy <= r; ++dy)
+                for (int dz = -r; dz <= r; ++dz)
+                    if (sqrt((double)(dx * dx + dy * dy + dz * dz)) <= lim) {
+                        host[n].x = (signed char)dx; host[n].y = (signed char)dy; host[n].z = (signed char)dz; host[n].w = 0;
+                        ++n;
+                    }
+        char4* d = nullptr;
+        if (cudaMalloc(&d, sizeof(char4) * n) != cudaSuccess) { free(host); return MAD_ERR_CUDA; }
+        if (cudaMemcpy(d, host, sizeof(char4) * n, cudaMemcpyHostToDevice) != cudaSuccess) { free(host); return MAD_ERR_CUDA; }
+        free(host);
+        g_mask_dev[r] = d;
+        g_mask_count[r] = n;
+    }
+    *dev = g_mask_dev[r];
+    *count = g_mask_count[r];
+    return MAD_OK;
+}
+
+extern "C" int mad_orient(const float* grad4_oct0, const float* grad4_oct1, const int* dims_oct_host,
+                          const MadKeypoint* kp, int n_kp, int r, const MadZoneTable* zones_host,
+                          const double* r1_table, int lim_main, int lim_sec, int32_t* n_ori, int32_t* slots,
+                          void* stream) {
+    MAD_CHECK_ARG(dims_oct_host && zones_host && r1_table && n_kp >= 0);
+    if (n_kp == 0) return MAD_OK;
+    MAD_CHECK_ARG(grad4_oct0 && grad4_oct1 && kp && n_ori && slots);
+    MAD_CHECK_ARG(zones_host->n_zones >= 3 && zones_host->n_zones <= 128 && zones_host->n_belts < 32);
+    MAD_CHECK_ARG(lim_main >= 0 && lim_main <= 6 && lim_sec >= 0 && lim_sec <= 6);
+    const char4* mask = nullptr;
+    int n_mask = 0;
+    int rc = ensure_mask(r, &mask, &n_mask);
+    if (rc != MAD_OK) { mad_set_error("mad_orient: cannot build the spherical mask for r=%d", r); return rc; }
+    OctDims d;
+    for (int o = 0; o < 2; ++o) for (int a = 0; a < 3; ++a) d.n[o][a] = dims_oct_host[3 * o + a];
+    ZoneTab T;
+    T.bounds = zones_host->bounds; T.belt_first = zones_host->belt_first; T.belt_phi = zones_host->belt_phi;
+    T.n_zones = zones_host->n_zones; T.n_belts = zones_host->n_belts;
+    const size_t smem = (size_t)n_mask * sizeof(float4);
+    if (smem > 200 * 1024) { mad_set_error("mad_orient: patch radius %d too large", r); return MAD_ERR_ARG; }
+    MAD_CUDA(cudaFuncSetAttribute(orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    orient_kernel<<<n_kp, 128, smem, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, r, mask,
+        n_mask, T, r1_table, lim_main, lim_sec, n_ori, slots);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}
+
+extern "C" size_t mad_compact_oriented_workspace_bytes(int n_kp) {
+    size_t b = 0;
+    cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, n_kp > 0 ? n_kp : 1);
+    return mad_align_up((size_t)(n_kp > 0 ? n_kp : 1) * sizeof(int), 256) + mad_align_up(b, 256);
+}
+
+extern "C" int mad_compact_oriented(const int32_t* n_ori, const int32_t* slots, int n_kp, MadOriented* oriented,
+                                    int cap, int* out_count, void* workspace, size_t workspace_bytes, void* stream) {
+    MAD_CHECK_ARG(out_count && n_kp >= 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n_kp == 0) {
+        MAD_CUDA(cudaMemsetAsync(out_count, 0, sizeof(int), st));
+        return MAD_OK;
+    }
+    MAD_CHECK_ARG(n_ori && slots && oriented && workspace && cap >= 0);
+    MAD_CHECK_ARG(workspace_bytes >= mad_compact_oriented_workspace_bytes(n_kp));
+    int* pos = reinterpret_cast<int*>(workspace);
+    char* cub_ws = reinterpret_cast<char*>(workspace) + mad_align_up((size_t)n_kp * sizeof(int), 256);
+    size_t cub_bytes = workspace_bytes - mad_align_up((size_t)n_kp * sizeof(int), 256);
+    MAD_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, n_ori, pos, n_kp, st));
+    compact_oriented_kernel<<<(int)mad_ceil_div(n_kp, 256), 256, 0, st>>>(n_ori, slots, pos, n_kp, oriented, cap, out_count);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}

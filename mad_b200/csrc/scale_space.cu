@@ -1,0 +1,637 @@
+// Scale-space stage of the MaD hot path for B200 (sm_100a):
+//   a1  zero padding                         (np.pad,                    mad/MapSpace.py:117-118)
+//   a2  2x cubic-spline upsampling + presmooth (interp1d cubic x3 + gaussian_filter, :137-146)
+//   a3  LoG response + a4 Gaussian grid        (gaussian_laplace / gaussian_filter, :170-173,182)
+//   a4  gradient field                         (np.gradient,              :187)
+// All kernels are HBM-bound stencils: marching kernels with register windows for the strided
+// axes (coalesced across the contiguous z index), shared-memory row staging for the z axis.
+#include "common.cuh"
+
+// ------------------------------------------------------------------------------------------
+// a1: zero padding
+// ------------------------------------------------------------------------------------------
+__global__ void pad3d_kernel(const float* __restrict__ in, int nx, int ny, int nz, int pad,
+                             float* __restrict__ out, long long total) {
+    const int oy = ny + 2 * pad, oz = nz + 2 * pad;
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        int z = (int)(g % oz);
+        long long t = g / oz;
+        int y = (int)(t % oy);
+        int x = (int)(t / oy);
+        int sx = x - pad, sy = y - pad, sz = z - pad;
+        float v = 0.f;
+        if (sx >= 0 && sx < nx && sy >= 0 && sy < ny && sz >= 0 && sz < nz)
+            v = __ldg(in + ((long long)sx * ny + sy) * nz + sz);
+        out[g] = v;
+    }
+}
+
+extern "C" int mad_pad3d(const float* in, int nx, int ny, int nz, int pad, float* out, void* stream) {
+    MAD_CHECK_ARG(in && out && nx > 0 && ny > 0 && nz > 0 && pad >= 0);
+    long long total = (long long)(nx + 2 * pad) * (ny + 2 * pad) * (nz + 2 * pad);
+    int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 16);
+    pad3d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, nx, ny, nz, pad, out, total);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// a2: not-a-knot cubic spline at half steps (+ Gaussian presmoothing along the same axis)
+//
+// Along one line y[0..n-1] with second derivatives M (unit spacing):
+//   M[i-1] + 4 M[i] + M[i+1] = 6 d_i,  d_i = y[i-1] - 2 y[i] + y[i+1]      (1 <= i <= n-2)
+//   not-a-knot: M[0]-2M[1]+M[2] = 0, M[n-3]-2M[n-2]+M[n-1] = 0  =>  M[1] = d_1, M[n-2] = d_{n-2}
+//   u[2i] = y[i],  u[2i+1] = (y[i]+y[i+1])/2 - (M[i]+M[i+1])/16
+// The remaining [1 4 1] system for M[2..n-3] is solved by the Thomas recurrence STREAMING:
+// the forward sweep is exact from the line start; the backward sweep for a chunk of 32 samples
+// starts 32 samples ahead, where the neglected term has decayed by (2-sqrt3)^32 = 5e-19, i.e.
+// below float64 rounding (and it starts from the true last row near the line end).  So no
+// O(n) scratch per line is needed: a 64-entry ring per thread in shared memory.
+// The presmoothing Gaussian (reflect boundary) of the same axis is applied on the fly to the
+// upsampled samples through a register window.  Separable operators on different axes commute,
+// so the per-axis fusion equals SciPy's "3 interpolations then 3 filters" up to f64 rounding.
+// ------------------------------------------------------------------------------------------
+struct SplineParams {
+    double cprime[40];  // Thomas pivots c'_i = 1/(4 - c'_{i-1}), c'_2 = 1/4 (constant beyond ~i=25)
+    double gw[9];       // presmoothing weights gw[|j|], j = 0..GR
+};
+
+template <int GR>
+struct GaussStream {
+    double w[2 * GR + 1];
+    int cnt;   // values pushed so far
+    int kout;  // next output index
+    __device__ __forceinline__ void init() {
+        cnt = 0;
+        kout = 0;
+#pragma unroll
+        for (int i = 0; i < 2 * GR + 1; ++i) w[i] = 0.0;
+    }
+    template <class IO>
+    __device__ __forceinline__ void emit(IO& io, const double* gw) {
+        double acc = w[GR] * gw[0];
+#pragma unroll
+        for (int jj = GR; jj >= 1; --jj) acc = fma(w[GR - jj] + w[GR + jj], gw[jj], acc);
+        io.put(kout++, acc);
+    }
+    template <class IO>
+    __device__ __forceinline__ void push(double v, IO& io, const double* gw) {
+        if (GR == 0) {
+            io.put(kout++, v);
+            return;
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * GR; ++i) w[i] = w[i + 1];
+        w[2 * GR] = v;
+        ++cnt;
+        if (cnt == GR + 1) {  // u[0..GR] sit in w[GR..2GR]: mirror them (reflect: u[-1-t] = u[t])
+#pragma unroll
+            for (int t = 0; t < GR; ++t) w[GR - 1 - t] = w[GR + t];
+            emit(io, gw);
+        } else if (cnt > GR + 1) {
+            emit(io, gw);
+        }
+    }
+    template <class IO>
+    __device__ __forceinline__ void finish(IO& io, const double* gw) {
+        if (GR == 0) return;
+        // virtual sample N+t equals u[N-1-t], which sits in slot 2GR-2t at that moment
+#pragma unroll
+        for (int t = 0; t < GR; ++t) push(w[2 * GR - 2 * t], io, gw);
+    }
+};
+
+template <int GR, class IO>
+__device__ __forceinline__ void spline_line(IO& io, const int n, const SplineParams& prm,
+                                            double* ring, const int rs) {
+    constexpr int C = 32, L = 32, RM = 63;
+    const int last = n - 3;
+    const double M1 = (io.y(0) - 2.0 * io.y(1)) + io.y(2);
+    const double Mn2 = (io.y(n - 3) - 2.0 * io.y(n - 2)) + io.y(n - 1);
+    double M2v = 0.0, Mn3v = 0.0;
+    int fwd = 2;
+    double xprev = 0.0;
+    double ya = io.y(1), yb = io.y(2);
+    GaussStream<GR> gs;
+    gs.init();
+    for (int s = 0; s < n; s += C) {
+        const int e = min(s + C, n);
+        const int top = min(e + L - 1, last);
+        while (fwd <= top) {  // forward Thomas sweep, loads batched 8 deep to keep HBM requests in flight
+            const int nb = min(8, top - fwd + 1);
+            double yy[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) yy[q] = (q < nb) ? io.y(fwd + 1 + q) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (q < nb) {
+                    const double yc = yy[q];
+                    double r = 6.0 * ((ya - 2.0 * yb) + yc);
+                    if (fwd == 2) r -= M1;
+                    if (fwd == last) r -= Mn2;
+                    const double x = (r - xprev) * prm.cprime[fwd < 39 ? fwd : 39];
+                    ring[(fwd & RM) * rs] = x;
+                    xprev = x;
+                    ya = yb;
+                    yb = yc;
+                    ++fwd;
+                }
+            }
+        }
+        const int lo = max(s, 2);
+        double Me = 0.0;
+        if (lo <= last) {
+            int j = top;
+            double M = ring[(j & RM) * rs];
+            for (;;) {
+                if (j == last) Mn3v = M;
+                if (j == 2) M2v = M;
+                if (j < e) ring[(j & RM) * rs] = M;
+                else if (j == e) Me = M;
+                if (j == lo) break;
+                --j;
+                M = fma(-prm.cprime[j < 39 ? j : 39], M, ring[(j & RM) * rs]);
+            }
+        }
+        auto Mval = [&](int i) -> double {
+            if (i == 0) return 2.0 * M1 - M2v;
+            if (i == 1) return M1;
+            if (i == n - 2) return Mn2;
+            if (i == n - 1) return 2.0 * Mn2 - Mn3v;
+            if (i == e) return Me;
+            return ring[(i & RM) * rs];
+        };
+        double Mi = Mval(s);
+        double yi = io.y(s);
+        for (int i0 = s; i0 < e; i0 += 8) {
+            double yy[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) yy[q] = (i0 + q < e && i0 + q + 1 < n) ? io.y(i0 + q + 1) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int i = i0 + q;
+                if (i < e) {
+                    gs.push(yi, io, prm.gw);
+                    if (i + 1 < n) {
+                        const double Mn = Mval(i + 1);
+                        const double yn = yy[q];
+                        gs.push(0.5 * (yi + yn) - (Mi + Mn) * 0.0625, io, prm.gw);
+                        Mi = Mn;
+                        yi = yn;
+                    }
+                }
+            }
+        }
+        io.chunk_done();
+    }
+    gs.finish(io, prm.gw);
+    io.chunk_done();
+}
+
+// Lines along a strided axis: thread (o, j) owns line  in[o*n*inner + j + i*inner].
+template <typename TIn, typename TOut>
+struct StridedIO {
+    const TIn* yin;
+    TOut* uout;
+    long long stride;
+    __device__ __forceinline__ double y(int i) const { return (double)__ldg(yin + (long long)i * stride); }
+    __device__ __forceinline__ void put(int k, double v) { uout[(long long)k * stride] = (TOut)v; }
+    __device__ __forceinline__ void chunk_done() {}
+};
+
+template <typename TIn, typename TOut, int GR>
+__global__ void __launch_bounds__(128)
+spline_up_strided_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int n, long long inner,
+                         long long total_lines, SplineParams prm) {
+    extern __shared__ double ring_s[];  // [64][blockDim.x]
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= total_lines) return;
+    const long long o = g / inner, j = g % inner;
+    StridedIO<TIn, TOut> io;
+    io.yin = in + o * (long long)n * inner + j;
+    io.uout = out + o * (long long)(2 * n - 1) * inner + j;
+    io.stride = inner;
+    spline_line<GR>(io, n, prm, ring_s + threadIdx.x, blockDim.x);
+}
+
+// Lines along the contiguous axis: one warp owns 32 consecutive lines; the input lines are staged
+// in shared memory with coalesced loads, outputs are staged per chunk and flushed row by row.
+constexpr int kZStage = 81;  // >= 2*32 outputs per chunk (+ GR at the end); odd row stride (in doubles) avoids bank conflicts
+struct ZLineIO {
+    const float* yline;   // this lane's line in shared memory
+    double* ostage;       // [32][kZStage]
+    double* out;          // global, first line of this warp
+    long long N;          // output line length (2n-1)
+    int lines_valid;      // lines of this warp that exist
+    int lane;
+    int kbase, cnt;
+    __device__ __forceinline__ double y(int i) const { return (double)yline[i]; }
+    __device__ __forceinline__ void put(int k, double v) {
+        ostage[lane * kZStage + (k - kbase)] = v;
+        ++cnt;
+    }
+    __device__ __forceinline__ void chunk_done() {
+        __syncwarp();
+        for (int r = 0; r < lines_valid; ++r)
+            for (int t = lane; t < cnt; t += 32) out[r * N + kbase + t] = ostage[r * kZStage + t];
+        kbase += cnt;
+        cnt = 0;
+        __syncwarp();
+    }
+};
+
+template <int GR>
+__global__ void __launch_bounds__(32)
+spline_up_z_kernel(const float* __restrict__ in, double* __restrict__ out, int n, long long total_lines,
+                   int npad, SplineParams prm) {
+    extern __shared__ double zs[];
+    double* ring = zs;                      // [64][32]
+    double* ostage = zs + 64 * 32;          // [32][kZStage]
+    float* ylines = reinterpret_cast<float*>(ostage + 32 * kZStage);  // [32][npad]
+    const int lane = threadIdx.x;
+    const long long l0 = (long long)blockIdx.x * 32;
+    const int valid = (int)min((long long)32, total_lines - l0);
+    for (int r = 0; r < 32; ++r) {
+        const long long line = l0 + min(r, valid - 1);   // tail lanes recompute the last line
+        for (int t = lane; t < n; t += 32) ylines[r * npad + t] = __ldg(in + line * n + t);
+    }
+    __syncwarp();
+    ZLineIO io;
+    io.yline = ylines + lane * npad;
+    io.ostage = ostage;
+    io.out = out + l0 * (long long)(2 * n - 1);
+    io.N = 2 * n - 1;
+    io.lines_valid = valid;
+    io.lane = lane;
+    io.kbase = 0;
+    io.cnt = 0;
+    spline_line<GR>(io, n, prm, ring + lane, 32);
+}
+
+static void fill_spline_params(SplineParams& p, const double* gw, int radius) {
+    p.cprime[0] = p.cprime[1] = 0.0;
+    p.cprime[2] = 0.25;
+    for (int i = 3; i < 40; ++i) p.cprime[i] = 1.0 / (4.0 - p.cprime[i - 1]);
+    for (int j = 0; j < 9; ++j) p.gw[j] = 0.0;
+    for (int j = 0; j <= radius; ++j) p.gw[j] = gw ? gw[radius + j] : (j == 0 ? 1.0 : 0.0);
+}
+
+extern "C" size_t mad_upsample_workspace_bytes(int bx, int by, int bz) {
+    size_t a = (size_t)bx * by * (2 * (size_t)bz - 1) * sizeof(double);
+    size_t b = (2 * (size_t)bx - 1) * by * (2 * (size_t)bz - 1) * sizeof(double);
+    return mad_align_up(a, 256) + mad_align_up(b, 256);
+}
+
+template <int GR>
+static int upsample_launch(const float* base, int bx, int by, int bz, const SplineParams& prm, float* up,
+                           double* wsA, double* wsB, cudaStream_t st) {
+    // pass Z (contiguous axis, smallest array): f32 [bx][by][bz] -> f64 [bx][by][2bz-1]
+    {
+        const long long lines = (long long)bx * by;
+        const int npad = bz | 1;
+        const size_t smem = (64 * 32 + 32 * kZStage) * sizeof(double) + (size_t)32 * npad * sizeof(float);
+        if (smem > 200 * 1024) {
+            mad_set_error("mad_upsample_presmooth: z extent %d too long for the shared-memory line stage", bz);
+            return MAD_ERR_ARG;
+        }
+        MAD_CUDA(cudaFuncSetAttribute(spline_up_z_kernel<GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        spline_up_z_kernel<GR><<<(unsigned)mad_ceil_div(lines, 32), 32, smem, st>>>(base, wsA, bz, lines, npad, prm);
+        MAD_LAUNCH_OK();
+    }
+    const size_t ring_smem = 64 * 128 * sizeof(double);
+    // pass X: f64 [bx][by][Z] -> f64 [2bx-1][by][Z],  Z = 2bz-1
+    {
+        const long long inner = (long long)by * (2 * bz - 1);
+        MAD_CUDA(cudaFuncSetAttribute(spline_up_strided_kernel<double, double, GR>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        spline_up_strided_kernel<double, double, GR>
+            <<<(unsigned)mad_ceil_div(inner, 128), 128, ring_smem, st>>>(wsA, wsB, bx, inner, inner, prm);
+        MAD_LAUNCH_OK();
+    }
+    // pass Y: f64 [X][by][Z] -> f32 [X][2by-1][Z],  X = 2bx-1
+    {
+        const long long inner = 2 * bz - 1;
+        const long long lines = (long long)(2 * bx - 1) * inner;
+        MAD_CUDA(cudaFuncSetAttribute(spline_up_strided_kernel<double, float, GR>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        spline_up_strided_kernel<double, float, GR>
+            <<<(unsigned)mad_ceil_div(lines, 128), 128, ring_smem, st>>>(wsB, up, by, inner, lines, prm);
+        MAD_LAUNCH_OK();
+    }
+    return MAD_OK;
+}
+
+extern "C" int mad_upsample_presmooth(const float* base, int bx, int by, int bz, const double* gauss_w_host,
+                                      int radius, float* up, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+    MAD_CHECK_ARG(base && up && workspace);
+    MAD_CHECK_ARG(bx >= 5 && by >= 5 && bz >= 5);
+    MAD_CHECK_ARG(radius >= 0 && radius <= 8 && (radius == 0 || gauss_w_host));
+    MAD_CHECK_ARG(2 * bx - 1 > radius && 2 * by - 1 > radius && 2 * bz - 1 > radius);
+    MAD_CHECK_ARG(workspace_bytes >= mad_upsample_workspace_bytes(bx, by, bz));
+    SplineParams prm;
+    fill_spline_params(prm, gauss_w_host, radius);
+    double* wsA = reinterpret_cast<double*>(workspace);
+    double* wsB = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) +
+                                            mad_align_up((size_t)bx * by * (2 * (size_t)bz - 1) * sizeof(double), 256));
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (radius) {
+        case 0: return upsample_launch<0>(base, bx, by, bz, prm, up, wsA, wsB, st);
+        case 1: return upsample_launch<1>(base, bx, by, bz, prm, up, wsA, wsB, st);
+        case 2: return upsample_launch<2>(base, bx, by, bz, prm, up, wsA, wsB, st);
+        case 3: return upsample_launch<3>(base, bx, by, bz, prm, up, wsA, wsB, st);
+        case 4: return upsample_launch<4>(base, bx, by, bz, prm, up, wsA, wsB, st);
+        case 6: return upsample_launch<6>(base, bx, by, bz, prm, up, wsA, wsB, st);
+        case 8: return upsample_launch<8>(base, bx, by, bz, prm, up, wsA, wsB, st);
+        default:
+            mad_set_error("mad_upsample_presmooth: presmoothing radius %d not instantiated (0-4, 6, 8)", radius);
+            return MAD_ERR_ARG;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// a3/a4: LoG + Gaussian with SciPy's pass structure.
+//   pass X:  f         -> P0 = g*f,  Q0 = g''*f
+//   pass Y:  P0, Q0    -> P01 = g*P0, R = g''*P0, S = g*Q0
+//   pass Z:  P01, R, S -> gauss = g*P01;  LoG = (g*S + g*R) + g''*P01;  out = max(0, -scale*LoG)
+// Every 1-D result is rounded to float32 (as SciPy stores it) before the next pass consumes it.
+// ------------------------------------------------------------------------------------------
+struct ConvW {
+    double w0[17];  // order-0 weights, index |j|
+    double w2[17];  // order-2 weights, index |j|
+};
+
+template <typename ACC> struct Wt;
+template <> struct Wt<double> { static __device__ __forceinline__ double get(double w) { return w; } };
+template <> struct Wt<float> { static __device__ __forceinline__ float get(double w) { return (float)w; } };
+
+template <int R, typename ACC>
+__device__ __forceinline__ void conv_both(const float* win, int t, const ConvW& w, float& o0, float& o2) {
+    const ACC c = (ACC)win[t + R];
+    ACC a0 = c * Wt<ACC>::get(w.w0[0]);
+    ACC a2 = c * Wt<ACC>::get(w.w2[0]);
+#pragma unroll
+    for (int jj = R; jj >= 1; --jj) {
+        const ACC s = (ACC)win[t + R - jj] + (ACC)win[t + R + jj];
+        a0 = fma(s, Wt<ACC>::get(w.w0[jj]), a0);
+        a2 = fma(s, Wt<ACC>::get(w.w2[jj]), a2);
+    }
+    o0 = (float)a0;
+    o2 = (float)a2;
+}
+
+template <int R, typename ACC>
+__device__ __forceinline__ float conv_g(const float* win, int t, const ConvW& w) {
+    ACC a0 = (ACC)win[t + R] * Wt<ACC>::get(w.w0[0]);
+#pragma unroll
+    for (int jj = R; jj >= 1; --jj) {
+        const ACC s = (ACC)win[t + R - jj] + (ACC)win[t + R + jj];
+        a0 = fma(s, Wt<ACC>::get(w.w0[jj]), a0);
+    }
+    return (float)a0;
+}
+
+// MODE 0: pass X (in0=f; o0=P0, o1=Q0).  MODE 1: pass Y (in0=P0, in1=Q0; o0=P01, o1=R, o2=S).
+template <int R, typename ACC, int MODE>
+__global__ void __launch_bounds__(128)
+log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ o0,
+                        float* __restrict__ o1, float* __restrict__ o2, int n, long long inner,
+                        long long total_lines, int seg_len, ConvW w) {
+    constexpr int T = 16, W = T + 2 * R;
+    const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (g >= total_lines) return;
+    const long long o = g / inner, j = g % inner;
+    const long long base = o * (long long)n * inner + j;
+    const int a0 = blockIdx.y * seg_len;
+    const int a1 = min(n, a0 + seg_len);
+    float wa[W];
+    float wb[MODE == 1 ? W : 1];
+#pragma unroll
+    for (int i = 0; i < 2 * R; ++i) {
+        const long long off = base + (long long)mad_reflect(a0 - R + i, n) * inner;
+        wa[i] = __ldg(in0 + off);
+        if (MODE == 1) wb[i] = __ldg(in1 + off);
+    }
+    for (int a = a0; a < a1; a += T) {
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const int pos = a + R + i;
+            float va = 0.f, vb = 0.f;
+            if (pos <= n - 1 + R) {
+                const long long off = base + (long long)mad_reflect(pos, n) * inner;
+                va = __ldg(in0 + off);
+                if (MODE == 1) vb = __ldg(in1 + off);
+            }
+            wa[2 * R + i] = va;
+            if (MODE == 1) wb[2 * R + i] = vb;
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            if (a + t < a1) {
+                const long long off = base + (long long)(a + t) * inner;
+                float r0, r2;
+                conv_both<R, ACC>(wa, t, w, r0, r2);
+                o0[off] = r0;
+                o1[off] = r2;
+                if (MODE == 1) o2[off] = conv_g<R, ACC>(wb, t, w);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * R; ++i) {
+            wa[i] = wa[i + T];
+            if (MODE == 1) wb[i] = wb[i + T];
+        }
+    }
+}
+
+template <int R, typename ACC>
+__global__ void __launch_bounds__(128)
+log_pass_z_kernel(const float* __restrict__ P01, const float* __restrict__ Rr, const float* __restrict__ S,
+                  float* __restrict__ log_out, float* __restrict__ gauss_out, int nz, long long n_rows,
+                  int rows_per_cta, int rs_in, int rs_out, float scale, ConvW w) {
+    constexpr int T = 8, W = T + 2 * R;
+    extern __shared__ __align__(16) float zsm[];
+    float* sin0 = zsm;
+    float* sin1 = sin0 + (size_t)rows_per_cta * rs_in;
+    float* sin2 = sin1 + (size_t)rows_per_cta * rs_in;
+    float* sout0 = sin2 + (size_t)rows_per_cta * rs_in;
+    float* sout1 = sout0 + (size_t)rows_per_cta * rs_out;
+    const long long row0 = (long long)blockIdx.x * rows_per_cta;
+    const int rows = (int)min((long long)rows_per_cta, n_rows - row0);
+    const int tid = threadIdx.x;
+    for (int r = 0; r < rows; ++r) {
+        const long long gb = (row0 + r) * nz;
+        for (int t = tid; t < rs_in; t += blockDim.x) {
+            float a = 0.f, b = 0.f, c = 0.f;
+            if (t < nz + 2 * R) {
+                const int z = mad_reflect(t - R, nz);
+                a = __ldg(P01 + gb + z);
+                b = __ldg(Rr + gb + z);
+                c = __ldg(S + gb + z);
+            }
+            sin0[r * rs_in + t] = a;
+            sin1[r * rs_in + t] = b;
+            sin2[r * rs_in + t] = c;
+        }
+    }
+    __syncthreads();
+    const int n_chunks = (nz + T - 1) / T;
+    for (int it = tid; it < rows * n_chunks; it += blockDim.x) {
+        const int r = it / n_chunks, c = it % n_chunks;
+        const int z0 = c * T;
+        float wa[W], wb[W], wc[W];
+        const float4* pa = reinterpret_cast<const float4*>(sin0 + r * rs_in + z0);
+        const float4* pb = reinterpret_cast<const float4*>(sin1 + r * rs_in + z0);
+        const float4* pc = reinterpret_cast<const float4*>(sin2 + r * rs_in + z0);
+#pragma unroll
+        for (int q = 0; q < W / 4; ++q) {
+            const float4 va = pa[q], vb = pb[q], vc = pc[q];
+            wa[4 * q] = va.x; wa[4 * q + 1] = va.y; wa[4 * q + 2] = va.z; wa[4 * q + 3] = va.w;
+            wb[4 * q] = vb.x; wb[4 * q + 1] = vb.y; wb[4 * q + 2] = vb.z; wb[4 * q + 3] = vb.w;
+            wc[4 * q] = vc.x; wc[4 * q + 1] = vc.y; wc[4 * q + 2] = vc.z; wc[4 * q + 3] = vc.w;
+        }
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            float gs, t3;
+            conv_both<R, ACC>(wa, t, w, gs, t3);
+            const float t2 = conv_g<R, ACC>(wb, t, w);
+            const float t1 = conv_g<R, ACC>(wc, t, w);
+            const float lap = __fadd_rn(__fadd_rn(t1, t2), t3);
+            float m = __fmul_rn(-lap, scale);
+            if (m < 0.f) m = 0.f;
+            if (z0 + t < nz) {
+                sout0[r * rs_out + z0 + t] = m;
+                sout1[r * rs_out + z0 + t] = gs;
+            }
+        }
+    }
+    __syncthreads();
+    for (int r = 0; r < rows; ++r) {
+        const long long gb = (row0 + r) * nz;
+        for (int t = tid; t < nz; t += blockDim.x) {
+            log_out[gb + t] = sout0[r * rs_out + t];
+            gauss_out[gb + t] = sout1[r * rs_out + t];
+        }
+    }
+}
+
+extern "C" size_t mad_log_gauss_workspace_bytes(int nx, int ny, int nz) {
+    const size_t v = mad_align_up((size_t)nx * ny * nz * sizeof(float), 256);
+    return 5 * v;  // P0, Q0, P01, R, S
+}
+
+template <int R, typename ACC>
+static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const ConvW& w, float scale, float* log_out,
+                            float* gauss_out, float* ws, cudaStream_t st) {
+    const size_t v = mad_align_up((size_t)nx * ny * nz * sizeof(float), 256) / sizeof(float);
+    float *P0 = ws, *Q0 = ws + v, *P01 = ws + 2 * v, *Rr = ws + 3 * v, *S = ws + 4 * v;
+    const int sms = mad_sm_count();
+    auto segs_for = [&](long long lines, int n) {
+        // enough CTAs to fill the machine (~8 CTAs of 128 threads per SM), segments multiple of 16
+        long long ctas = mad_ceil_div(lines, 128);
+        int segs = (int)std::max<long long>(1, std::min<long long>(mad_ceil_div((long long)sms * 8, ctas), mad_ceil_div(n, 64)));
+        int seg_len = (int)mad_ceil_div(mad_ceil_div(n, segs), 16) * 16;
+        return seg_len;
+    };
+    {
+        const long long inner = (long long)ny * nz;
+        const int seg_len = segs_for(inner, nx);
+        dim3 grid_dim((unsigned)mad_ceil_div(inner, 128), (unsigned)mad_ceil_div(nx, seg_len));
+        log_pass_strided_kernel<R, ACC, 0><<<grid_dim, 128, 0, st>>>(grid, nullptr, P0, Q0, nullptr, nx, inner, inner, seg_len, w);
+        MAD_LAUNCH_OK();
+    }
+    {
+        const long long inner = nz;
+        const long long lines = (long long)nx * nz;
+        const int seg_len = segs_for(lines, ny);
+        dim3 grid_dim((unsigned)mad_ceil_div(lines, 128), (unsigned)mad_ceil_div(ny, seg_len));
+        log_pass_strided_kernel<R, ACC, 1><<<grid_dim, 128, 0, st>>>(P0, Q0, P01, Rr, S, ny, inner, lines, seg_len, w);
+        MAD_LAUNCH_OK();
+    }
+    {
+        const long long n_rows = (long long)nx * ny;
+        const int n_chunks = (nz + 7) / 8;
+        const int rs_in = (n_chunks * 8 + 2 * R + 3) / 4 * 4;
+        const int rs_out = (nz + 3) / 4 * 4;
+        const size_t row_bytes = (size_t)(3 * rs_in + 2 * rs_out) * sizeof(float);
+        int rows = (int)std::max<long long>(1, std::min<long long>(mad_ceil_div(256, n_chunks), (long long)(48 * 1024 / row_bytes)));
+        const size_t smem = rows * row_bytes;
+        if (smem > 200 * 1024) {
+            mad_set_error("mad_log_gauss: z extent %d too long for the shared-memory row stage", nz);
+            return MAD_ERR_ARG;
+        }
+        MAD_CUDA(cudaFuncSetAttribute(log_pass_z_kernel<R, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        log_pass_z_kernel<R, ACC><<<(unsigned)mad_ceil_div(n_rows, rows), 128, smem, st>>>(P01, Rr, S, log_out, gauss_out, nz, n_rows, rows, rs_in, rs_out, scale, w);
+        MAD_LAUNCH_OK();
+    }
+    return MAD_OK;
+}
+
+extern "C" int mad_log_gauss(const float* grid, int nx, int ny, int nz, const double* w0_host, const double* w2_host,
+                             int radius, float scale, float* log_out, float* gauss_out, void* workspace,
+                             size_t workspace_bytes, int exact_f64, void* stream) {
+    MAD_CHECK_ARG(grid && log_out && gauss_out && workspace && w0_host && w2_host);
+    MAD_CHECK_ARG(radius >= 1 && radius <= 16);
+    MAD_CHECK_ARG(nx >= 2 * radius + 1 && ny >= 2 * radius + 1 && nz >= 2 * radius + 1);
+    MAD_CHECK_ARG(workspace_bytes >= mad_log_gauss_workspace_bytes(nx, ny, nz));
+    ConvW w;
+    for (int j = 0; j < 17; ++j) w.w0[j] = w.w2[j] = 0.0;
+    for (int j = 0; j <= radius; ++j) {
+        w.w0[j] = w0_host[radius + j];
+        w.w2[j] = w2_host[radius + j];
+    }
+    float* ws = reinterpret_cast<float*>(workspace);
+    cudaStream_t st = (cudaStream_t)stream;
+#define MAD_LOG_CASE(RR)                                                                                   \
+    case RR:                                                                                               \
+        return exact_f64 ? log_gauss_launch<RR, double>(grid, nx, ny, nz, w, scale, log_out, gauss_out, ws, st) \
+                         : log_gauss_launch<RR, float>(grid, nx, ny, nz, w, scale, log_out, gauss_out, ws, st);
+    switch (radius) {
+        MAD_LOG_CASE(4)
+        MAD_LOG_CASE(6)
+        MAD_LOG_CASE(8)
+        MAD_LOG_CASE(10)
+        MAD_LOG_CASE(12)
+        default:
+            mad_set_error("mad_log_gauss: kernel radius %d not instantiated (4, 6, 8, 10, 12)", radius);
+            return MAD_ERR_ARG;
+    }
+#undef MAD_LOG_CASE
+}
+
+// ------------------------------------------------------------------------------------------
+// a4: gradient field, float4 (gx, gy, gz, 0) per voxel
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ float grad_axis(const float* __restrict__ f, long long c, int i, int n, long long stride) {
+    if (i == 0) return __fsub_rn(__ldg(f + c + stride), __ldg(f + c));
+    if (i == n - 1) return __fsub_rn(__ldg(f + c), __ldg(f + c - stride));
+    return __fmul_rn(__fsub_rn(__ldg(f + c + stride), __ldg(f + c - stride)), 0.5f);
+}
+
+__global__ void __launch_bounds__(256)
+gradient_kernel(const float* __restrict__ f, int nx, int ny, int nz, float4* __restrict__ grad, long long total) {
+    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
+         g += (long long)gridDim.x * blockDim.x) {
+        const int z = (int)(g % nz);
+        const long long t = g / nz;
+        const int y = (int)(t % ny);
+        const int x = (int)(t / ny);
+        float4 v;
+        v.x = grad_axis(f, g, x, nx, (long long)ny * nz);
+        v.y = grad_axis(f, g, y, ny, nz);
+        v.z = grad_axis(f, g, z, nz, 1);
+        v.w = 0.f;
+        grad[g] = v;
+    }
+}
+
+extern "C" int mad_gradient(const float* gauss, int nx, int ny, int nz, float* grad4, void* stream) {
+    MAD_CHECK_ARG(gauss && grad4 && nx >= 2 && ny >= 2 && nz >= 2);
+    MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad4) & 15) == 0);
+    const long long total = (long long)nx * ny * nz;
+    const int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 32);
+    gradient_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gauss, nx, ny, nz, reinterpret_cast<float4*>(grad4), total);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}

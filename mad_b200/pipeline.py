@@ -1,0 +1,363 @@
+"""Array-level host API of the B200 hot path: device memory and streams come from PyTorch, all
+arithmetic happens in libmad_b200.so (hand-written sm_100a CUDA) through the C ABI.
+
+    space = build_space(grid)                 # a1-a4  (mad/MapSpace.py:116-189)
+    kp    = detect(space)                     # a5-a6  (mad/Detector.py:18-128)
+    ori   = orient(space, kp)                 # a7-a10 (mad/Orientator.py:68-343)
+    dsc   = describe(space, kp, ori)          # a11-a12 (mad/Descriptor.py:106-202)
+    pairs = match_threshold(hi_dsc, lo_dsc)   # a15    (mad/MaD.py:416-424)
+
+The reference-shaped classes (MapSpace, Detector, Orientator, Descriptor) are thin wrappers over
+these functions.  Nothing here computes on the CPU: without a CUDA device every call raises.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from . import tables
+from ._lib import call, KEYPOINT_DTYPE, ORIENTED_DTYPE, MAX_ORI, DSC_LEN
+
+LAUNCHES = {"n": 0}     # kernels launched by this library (bench.py reports it)
+
+
+def _count(n):
+    LAUNCHES["n"] += n
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.MadError("mad_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+def _dptr(a):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class _DeviceTables(object):
+    """Zone / rotation tables resident on one device."""
+
+    def __init__(self, device, ori_zones=112, dsc_zones=16):
+        self.device = device
+        self.keep = []
+        self.z_ori = self._zone_struct(tables.zone_tables(ori_zones))
+        self.z_dsc = self._zone_struct(tables.zone_tables(dsc_zones))
+        ot = tables.orientation_tables(ori_zones)
+        self.ori_zones = ori_zones
+        self.r1 = torch.from_numpy(np.ascontiguousarray(ot.r1.reshape(-1, 9))).to(device)
+        self.rf = torch.from_numpy(np.ascontiguousarray(ot.rf.reshape(-1, 9))).to(device)
+        self.rf_inv = torch.from_numpy(np.ascontiguousarray(ot.rf_inv.reshape(-1, 9))).to(device)
+
+    def _zone_struct(self, zt):
+        b = torch.from_numpy(np.ascontiguousarray(zt.bounds)).to(self.device)
+        f = torch.from_numpy(np.ascontiguousarray(zt.belt_first)).to(self.device)
+        p = torch.from_numpy(np.ascontiguousarray(zt.belt_phi)).to(self.device)
+        self.keep += [b, f, p]
+        s = _lib.MadZoneTable()
+        s.n_zones, s.n_belts = zt.size, zt.n_belts
+        s.bounds, s.belt_first, s.belt_phi = b.data_ptr(), f.data_ptr(), p.data_ptr()
+        return s
+
+
+_TABLE_CACHE = {}
+
+
+def device_tables(device):
+    key = (str(device),)
+    if key not in _TABLE_CACHE:
+        _TABLE_CACHE[key] = _DeviceTables(device)
+    return _TABLE_CACHE[key]
+
+
+class Space(object):
+    """Device-resident scale space of one map (both octaves): what MapSpace.build_space makes."""
+
+    def __init__(self):
+        self.grids = []      # [up, base]           f32 [x][y][z]
+        self.logs = []       # map_space            f32
+        self.gauss = []      # gauss_list           f32
+        self.grad4 = []      # grad_list as float4  f32 [x][y][z][4]
+        self.dims = []
+        self.n_input_voxels = 0
+
+    @property
+    def dims_host(self):
+        return np.array([d for o in self.dims for d in o], dtype=np.int32)
+
+
+def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True, keep_gauss=True):
+    """a1-a4.  ``grid``: float32 [x][y][z], torch CUDA tensor or NumPy array (copied to the device)."""
+    _require_cuda()
+    if isinstance(grid, np.ndarray):
+        grid = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float32)).cuda()
+    grid = grid.contiguous().float()
+    dev = grid.device
+    st = _stream()
+    nx, ny, nz = grid.shape
+    sp = Space()
+    sp.n_input_voxels = nx * ny * nz
+    if map_padding:
+        bx, by, bz = nx + 2 * map_padding, ny + 2 * map_padding, nz + 2 * map_padding
+        base = torch.empty((bx, by, bz), dtype=torch.float32, device=dev)
+        call("mad_pad3d", _ptr(grid), nx, ny, nz, int(map_padding), _ptr(base), st)
+        _count(1)
+    else:
+        bx, by, bz = nx, ny, nz
+        base = grid
+    # a2: 2x upsampled octave
+    ux, uy, uz = 2 * bx - 1, 2 * by - 1, 2 * bz - 1
+    up = torch.empty((ux, uy, uz), dtype=torch.float32, device=dev)
+    ws_bytes = _lib.lib.mad_upsample_workspace_bytes(bx, by, bz)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    if sig_presmooth:
+        rad = tables.gaussian_radius(sig_presmooth)
+        gw = np.ascontiguousarray(tables.gaussian_weights(sig_presmooth, 0, rad))
+        call("mad_upsample_presmooth", _ptr(base), bx, by, bz, _dptr(gw), rad, _ptr(up), _ptr(ws), ws_bytes, st)
+    else:
+        call("mad_upsample_presmooth", _ptr(base), bx, by, bz, C.c_void_p(0), 0, _ptr(up), _ptr(ws), ws_bytes, st)
+    _count(3)
+    del ws
+    sp.grids = [up, base]
+    sp.dims = [(ux, uy, uz), (bx, by, bz)]
+    # a3/a4 per octave
+    rad = tables.gaussian_radius(sig_init)
+    w0 = np.ascontiguousarray(tables.gaussian_weights(sig_init, 0, rad))
+    w2 = np.ascontiguousarray(tables.gaussian_weights(sig_init, 2, rad))
+    scale = float(np.float32(sig_init ** 2))
+    for g, (gx, gy, gz) in zip(sp.grids, sp.dims):
+        ws_bytes = _lib.lib.mad_log_gauss_workspace_bytes(gx, gy, gz)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        lg = torch.empty((gx, gy, gz), dtype=torch.float32, device=dev)
+        gs = torch.empty((gx, gy, gz), dtype=torch.float32, device=dev)
+        call("mad_log_gauss", _ptr(g), gx, gy, gz, _dptr(w0), _dptr(w2), rad, C.c_float(scale), _ptr(lg), _ptr(gs),
+             _ptr(ws), ws_bytes, 1 if exact_f64 else 0, st)
+        del ws
+        gr = torch.empty((gx, gy, gz, 4), dtype=torch.float32, device=dev)
+        call("mad_gradient", _ptr(gs), gx, gy, gz, _ptr(gr), st)
+        _count(4)
+        sp.logs.append(lg)
+        sp.gauss.append(gs if keep_gauss else None)
+        sp.grad4.append(gr)
+    return sp
+
+
+class Keypoints(object):
+    """Accepted keypoints in canonical order; device table (MadKeypoint[K]) + lazy host copy."""
+
+    def __init__(self, table, count):
+        self.table = table          # torch int32 [cap, 12] on the device
+        self.count = int(count)
+        self._host = None
+
+    def host(self):
+        if self._host is None:
+            self._host = self.table[:self.count].cpu().numpy().view(KEYPOINT_DTYPE).reshape(-1)
+        return self._host
+
+    def __len__(self):
+        return self.count
+
+
+def keypoints_from_host(arr, device):
+    arr = np.ascontiguousarray(arr, dtype=KEYPOINT_DTYPE)
+    t = torch.from_numpy(arr.view(np.int32).reshape(-1, 12).copy()).to(device)
+    k = Keypoints(t, len(arr))
+    k._host = arr
+    return k
+
+
+def detect(space, border=12, threshold=5e-2, cap=None):
+    """a5/a6 on both octaves, canonical order, accepted keypoints only."""
+    _require_cuda()
+    dev = space.logs[0].device
+    st = _stream()
+    if cap is None:
+        cap = 1 << 16
+    while True:
+        cand = torch.empty((cap, 12), dtype=torch.int32, device=dev)
+        counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        for o, (lg, (gx, gy, gz)) in enumerate(zip(space.logs, space.dims)):
+            call("mad_detect", _ptr(lg), gx, gy, gz, o, int(border), C.c_float(threshold), _ptr(cand), cap,
+                 _ptr(counter), st)
+            _count(1)
+        n = int(counter.item())
+        if n <= cap:
+            break
+        cap = int(n * 1.25) + 16        # rare: candidate list overflowed, redo with room
+    out = torch.empty((max(n, 1), 12), dtype=torch.int32, device=dev)
+    out_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = _lib.lib.mad_sort_keypoints_workspace_bytes(n)
+    ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
+    dims = space.dims_host
+    call("mad_sort_keypoints", _ptr(cand), n, _dptr(dims), _ptr(out), _ptr(out_count), _ptr(ws), ws_bytes, st)
+    _count(5)
+    return Keypoints(out, out_count.item())
+
+
+class Oriented(object):
+    def __init__(self, table, count):
+        self.table = table          # torch int32 [cap, 2] on the device (MadOriented)
+        self.count = int(count)
+        self._host = None
+
+    def host(self):
+        if self._host is None:
+            self._host = self.table[:self.count].cpu().numpy().view(ORIENTED_DTYPE).reshape(-1)
+        return self._host
+
+    def __len__(self):
+        return self.count
+
+
+def oriented_from_host(arr, device):
+    arr = np.ascontiguousarray(arr, dtype=ORIENTED_DTYPE)
+    t = torch.from_numpy(arr.view(np.int32).reshape(-1, 2).copy()).to(device)
+    o = Oriented(t, len(arr))
+    o._host = arr
+    return o
+
+
+def orient(space, kp, radius=8, lim_main=6, lim_sec=6):
+    """a7-a10: per keypoint up to 36 (main, sec) pairs, compacted in emission order."""
+    _require_cuda()
+    dev = space.grad4[0].device
+    st = _stream()
+    tb = device_tables(dev)
+    n = len(kp)
+    if n == 0:
+        return Oriented(torch.empty((1, 2), dtype=torch.int32, device=dev), 0)
+    n_ori = torch.empty(n, dtype=torch.int32, device=dev)
+    slots = torch.empty((n, MAX_ORI), dtype=torch.int32, device=dev)
+    dims = space.dims_host
+    call("mad_orient", _ptr(space.grad4[0]), _ptr(space.grad4[1]), _dptr(dims), _ptr(kp.table), n, int(radius),
+         C.byref(tb.z_ori), _ptr(tb.r1), int(lim_main), int(lim_sec), _ptr(n_ori), _ptr(slots), st)
+    cap = n * MAX_ORI
+    out = torch.empty((cap, 2), dtype=torch.int32, device=dev)
+    out_count = torch.zeros(1, dtype=torch.int32, device=dev)
+    ws_bytes = _lib.lib.mad_compact_oriented_workspace_bytes(n)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("mad_compact_oriented", _ptr(n_ori), _ptr(slots), n, _ptr(out), cap, _ptr(out_count), _ptr(ws), ws_bytes, st)
+    _count(3)
+    return Oriented(out, out_count.item())
+
+
+def describe(space, kp, ori, radius=8):
+    """a11/a12: int16 [D, 1024] descriptors on the device."""
+    _require_cuda()
+    dev = space.grad4[0].device
+    st = _stream()
+    tb = device_tables(dev)
+    d = len(ori)
+    dsc = torch.empty((d, DSC_LEN), dtype=torch.int16, device=dev)
+    if d == 0:
+        return dsc
+    dims = space.dims_host
+    call("mad_describe", _ptr(space.grad4[0]), _ptr(space.grad4[1]), _dptr(dims), _ptr(kp.table), _ptr(ori.table), d,
+         int(radius), C.byref(tb.z_dsc), _ptr(tb.rf), _ptr(tb.rf_inv), tb.ori_zones, _ptr(dsc), st)
+    _count(1)
+    return dsc
+
+
+def describe_struct(grid, patch_size=16, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True):
+    """The whole a1-a12 chain of ``MaD._describe_struct`` (mad/MaD.py:358-368) on device arrays."""
+    r = (patch_size - patch_size % 2) // 2
+    sp = build_space(grid, map_padding, sig_init, sig_presmooth, exact_f64=exact_f64, keep_gauss=False)
+    kp = detect(sp)
+    ori = orient(sp, kp, r)
+    dsc = describe(sp, kp, ori, r)
+    return sp, kp, ori, dsc
+
+
+# ---------------------------------------------------------------------------------------------
+# a15 matching
+# ---------------------------------------------------------------------------------------------
+class DescriptorSet(object):
+    """int16 descriptors prepared for matching: exact norms (+ fp16 operand for tcgen05)."""
+
+    def __init__(self, dsc, need_half=True):
+        _require_cuda()
+        if isinstance(dsc, np.ndarray):
+            dsc = torch.from_numpy(np.ascontiguousarray(dsc, dtype=np.int16)).cuda()
+        self.dsc = dsc.contiguous()
+        assert self.dsc.dtype == torch.int16 and self.dsc.dim() == 2 and self.dsc.shape[1] == DSC_LEN
+        dev = self.dsc.device
+        st = _stream()
+        self.rows = self.dsc.shape[0]
+        self.rows_padded = (self.rows + 127) // 128 * 128
+        self.norm2 = torch.empty(max(self.rows, 1), dtype=torch.int32, device=dev)
+        call("mad_dsc_norms", _ptr(self.dsc), self.rows, _ptr(self.norm2), st)
+        _count(1)
+        self.half = None
+        if need_half:
+            self.half = torch.empty((max(self.rows_padded, 128), DSC_LEN), dtype=torch.float16, device=dev)
+            call("mad_dsc_to_half", _ptr(self.dsc), self.rows, self.rows_padded, _ptr(self.half), st)
+            _count(1)
+        s = _lib.MadDscSet()
+        s.dsc = self.dsc.data_ptr()
+        s.half = self.half.data_ptr() if self.half is not None else 0
+        s.norm2 = self.norm2.data_ptr()
+        s.rows, s.rows_padded = self.rows, self.rows_padded
+        self.c = s
+
+
+def _as_set(x, impl):
+    return x if isinstance(x, DescriptorSet) else DescriptorSet(x, need_half=(impl == 0))
+
+
+def match_threshold(hi, lo, cc=0.6, impl=0):
+    """Pairs (i, j) with cosine(hi_i, lo_j) > cc in row-major order (mad/MaD.py:420-424).
+    Returns (hi index int32 [P], lo index int32 [P], score float64 [P]) as device tensors."""
+    hi, lo = _as_set(hi, impl), _as_set(lo, impl)
+    dev = hi.dsc.device
+    st = _stream()
+    m = hi.rows
+    if m == 0 or lo.rows == 0:
+        e = torch.empty(0, dtype=torch.int32, device=dev)
+        return e, e.clone(), torch.empty(0, dtype=torch.float64, device=dev)
+    row_count = torch.empty(m, dtype=torch.int32, device=dev)
+    call("mad_match_count", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), _ptr(row_count), impl, st)
+    row_off = torch.empty(m, dtype=torch.int64, device=dev)
+    total = torch.zeros(1, dtype=torch.int64, device=dev)
+    ws_bytes = _lib.lib.mad_exclusive_scan_workspace_bytes(m)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("mad_exclusive_scan_i32_to_i64", _ptr(row_count), m, _ptr(row_off), _ptr(total), _ptr(ws), ws_bytes, st)
+    p = int(total.item())
+    pair_hi = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
+    pair_lo = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
+    score = torch.empty(max(p, 1), dtype=torch.float64, device=dev)
+    call("mad_match_fill", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), _ptr(row_off), _ptr(pair_hi), _ptr(pair_lo),
+         _ptr(score), impl, st)
+    _count(4)
+    return pair_hi[:p], pair_lo[:p], score[:p]
+
+
+def match_topk(hi, lo, k=8, lo_index_base=0, impl=0):
+    """Per hi row the k best lo rows by (score desc, index asc).  Device tensors (idx, score)."""
+    hi, lo = _as_set(hi, impl), _as_set(lo, impl)
+    dev = hi.dsc.device
+    st = _stream()
+    idx = torch.empty((hi.rows, k), dtype=torch.int32, device=dev)
+    score = torch.empty((hi.rows, k), dtype=torch.float64, device=dev)
+    call("mad_match_topk", C.byref(hi.c), C.byref(lo.c), int(k), int(lo_index_base), _ptr(idx), _ptr(score), impl, st)
+    _count(1)
+    return idx, score
+
+
+def topk_merge(idx_g, score_g):
+    """[G, M, k] per-shard lists -> merged [M, k]."""
+    g, m, k = idx_g.shape
+    dev = idx_g.device
+    idx = torch.empty((m, k), dtype=torch.int32, device=dev)
+    score = torch.empty((m, k), dtype=torch.float64, device=dev)
+    call("mad_topk_merge", _ptr(idx_g.contiguous()), _ptr(score_g.contiguous()), g, m, k, _ptr(idx), _ptr(score), _stream())
+    _count(1)
+    return idx, score
