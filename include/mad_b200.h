@@ -68,6 +68,18 @@ int mad_version(void);
 /* Fills (sm_count, cc_major, cc_minor) of the current device. */
 int mad_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* ---- launch accounting and per-kernel timing (no reference counterpart; measurement only) ---- */
+/* Number of kernels this library has launched in this process (CUB-internal kernels count as one
+ * per CUB call). */
+long long mad_launch_count(void);
+/* While enabled, every kernel launch is bracketed by two CUDA events on its stream.  Records
+ * accumulate until mad_profile_reset(); mad_profile_get(i) synchronises on record i and returns
+ * the kernel's name (static string) and its duration in milliseconds. */
+int mad_profile_enable(int on);
+int mad_profile_count(void);
+int mad_profile_get(int i, const char** name, float* ms);
+int mad_profile_reset(void);
+
 /* ---- a1: zero padding (np.pad, mad/MapSpace.py:117-118) ---------------------------------- */
 int mad_pad3d(const float* in, int nx, int ny, int nz, int pad, float* out, void* stream);
 

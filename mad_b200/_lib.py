@@ -51,6 +51,11 @@ SIGNATURES = {
     "mad_last_error_string": (C.c_char_p, []),
     "mad_version": (_I, []),
     "mad_device_info": (_I, [C.POINTER(_I), C.POINTER(_I), C.POINTER(_I)]),
+    "mad_launch_count": (C.c_longlong, []),
+    "mad_profile_enable": (_I, [_I]),
+    "mad_profile_count": (_I, []),
+    "mad_profile_get": (_I, [_I, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
+    "mad_profile_reset": (_I, []),
     "mad_pad3d": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "mad_upsample_workspace_bytes": (_SZ, [_I, _I, _I]),
     "mad_upsample_presmooth": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _SZ, _P]),

@@ -28,6 +28,59 @@ int mad_sm_count() {
     return cached;
 }
 
+// ---- launch accounting + optional per-launch event timing ---------------------------------------
+#include <atomic>
+#include <mutex>
+#include <vector>
+namespace {
+struct ProfRec { const char* name; cudaEvent_t a, b; };
+std::atomic<long long> g_launches{0};
+std::atomic<int> g_prof_on{0};
+std::mutex g_prof_mu;
+std::vector<ProfRec> g_prof;
+}  // namespace
+
+MadProfScope::MadProfScope(const char* name, cudaStream_t stream) : slot(-1), st(stream) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    if (!g_prof_on.load(std::memory_order_relaxed)) return;
+    ProfRec r;
+    r.name = name;
+    if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess) return;
+    cudaEventRecord(r.a, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+    slot = (int)g_prof.size() - 1;
+}
+MadProfScope::~MadProfScope() {
+    if (slot < 0) return;
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    cudaEventRecord(g_prof[slot].b, st);
+}
+
+extern "C" long long mad_launch_count(void) { return g_launches.load(); }
+extern "C" int mad_profile_enable(int on) {
+    g_prof_on.store(on ? 1 : 0);
+    return MAD_OK;
+}
+extern "C" int mad_profile_count(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    return (int)g_prof.size();
+}
+extern "C" int mad_profile_get(int i, const char** name, float* ms) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    MAD_CHECK_ARG(name && ms && i >= 0 && i < (int)g_prof.size());
+    MAD_CUDA(cudaEventSynchronize(g_prof[i].b));
+    MAD_CUDA(cudaEventElapsedTime(ms, g_prof[i].a, g_prof[i].b));
+    *name = g_prof[i].name;
+    return MAD_OK;
+}
+extern "C" int mad_profile_reset(void) {
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    return MAD_OK;
+}
+
 extern "C" const char* mad_last_error_string(void) { return g_err; }
 extern "C" int mad_version(void) { return 100; }
 

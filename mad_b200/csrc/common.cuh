@@ -38,3 +38,15 @@ __host__ __device__ __forceinline__ int mad_reflect(int i, int n) {
 }
 
 int mad_sm_count();
+
+// ---- launch accounting / optional per-kernel CUDA-event timing (mad_profile_*, api.cu) ----------
+// Every kernel launch site of the library opens a MadProfScope: it always counts the launch
+// (mad_launch_count) and, while profiling is enabled, brackets it with two events recorded on
+// the launching stream.  bench.py reads the per-kernel durations from there.
+struct MadProfScope {
+    int slot;
+    cudaStream_t st;
+    MadProfScope(const char* name, cudaStream_t stream);
+    ~MadProfScope();
+};
+#define MAD_PROF(name, stream) MadProfScope _mad_prof_scope(name, (cudaStream_t)(stream))

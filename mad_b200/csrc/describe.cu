@@ -115,6 +115,7 @@ extern "C" int mad_describe(const float* grad4_oct0, const float* grad4_oct1, co
     ZoneTab T;
     T.bounds = zones_host->bounds; T.belt_first = zones_host->belt_first; T.belt_phi = zones_host->belt_phi;
     T.n_zones = zones_host->n_zones; T.n_belts = zones_host->n_belts;
+    MAD_PROF("describe_kernel", stream);
     describe_kernel<<<n_oriented, 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, oriented, r,
         T, rf_table, rf_inv_table, rf_zones, dsc);

@@ -210,6 +210,7 @@ extern "C" int mad_detect(const float* log_grid, int nx, int ny, int nz, int oct
     if (nx <= 2 * border || ny <= 2 * border || nz <= 2 * border) return MAD_OK;  // nothing can be detected
     const long long total = (long long)(nx - 2 * border) * (ny - 2 * border) * (nz - 2 * border);
     const int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 32);
+    MAD_PROF("detect_kernel", stream);
     detect_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(log_grid, nx, ny, nz, oct, border, threshold, cand, cap, count);
     MAD_LAUNCH_OK();
     return MAD_OK;
@@ -236,14 +237,27 @@ extern "C" int mad_sort_keypoints(const MadKeypoint* cand, int n, const int* dim
     int* flags = reinterpret_cast<int*>(ws + l.flags);
     int* pos = reinterpret_cast<int*>(ws + l.pos);
     const int tb = 256, nb = (int)mad_ceil_div(n, tb);
-    build_keys_kernel<<<nb, tb, 0, st>>>(cand, n, dims_oct_host[1], dims_oct_host[2], dims_oct_host[4], dims_oct_host[5], keys_in, idx_in);
-    MAD_LAUNCH_OK();
+    {
+        MAD_PROF("build_keys_kernel", st);
+        build_keys_kernel<<<nb, tb, 0, st>>>(cand, n, dims_oct_host[1], dims_oct_host[2], dims_oct_host[4], dims_oct_host[5], keys_in, idx_in);
+        MAD_LAUNCH_OK();
+    }
     size_t cub_bytes = l.total - l.cub;
-    MAD_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 64, st));
-    flags_kernel<<<nb, tb, 0, st>>>(cand, idx_out, n, flags);
-    MAD_LAUNCH_OK();
+    {
+        MAD_PROF("cub_radix_sort_pairs", st);
+        MAD_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 64, st));
+    }
+    {
+        MAD_PROF("flags_kernel", st);
+        flags_kernel<<<nb, tb, 0, st>>>(cand, idx_out, n, flags);
+        MAD_LAUNCH_OK();
+    }
     cub_bytes = l.total - l.cub;
-    MAD_CUDA(cub::DeviceScan::ExclusiveSum(ws + l.cub, cub_bytes, flags, pos, n, st));
+    {
+        MAD_PROF("cub_exclusive_sum", st);
+        MAD_CUDA(cub::DeviceScan::ExclusiveSum(ws + l.cub, cub_bytes, flags, pos, n, st));
+    }
+    MAD_PROF("scatter_kernel", st);
     scatter_kernel<<<nb, tb, 0, st>>>(cand, idx_out, flags, pos, n, out, out_count);
     MAD_LAUNCH_OK();
     return MAD_OK;

@@ -143,6 +143,7 @@ extern "C" int mad_dsc_norms(const int16_t* dsc, int rows, int32_t* norm2, void*
     MAD_CHECK_ARG(rows >= 0);
     if (rows == 0) return MAD_OK;
     MAD_CHECK_ARG(dsc && norm2);
+    MAD_PROF("norms_kernel", stream);
     norms_kernel<<<(int)mad_ceil_div((long long)rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(dsc, rows, norm2);
     MAD_LAUNCH_OK();
     return MAD_OK;
@@ -154,6 +155,7 @@ extern "C" int mad_dsc_to_half(const int16_t* dsc, int rows, int rows_padded, vo
     MAD_CHECK_ARG(dsc && half_out);
     const long long total = (long long)rows_padded * MAD_DSC_LEN;
     const int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 16);
+    MAD_PROF("to_half_kernel", stream);
     to_half_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(dsc, rows, rows_padded, reinterpret_cast<__half*>(half_out));
     MAD_LAUNCH_OK();
     return MAD_OK;
@@ -163,6 +165,7 @@ int mad_match_simt(const int16_t* hi, int M, const int16_t* lo, int N, const int
                    double cc, int mode, int32_t* row_count, const int64_t* row_offset, int32_t* pair_hi,
                    int32_t* pair_lo, double* pair_score, int k, int lo_index_base, int32_t* topk_idx,
                    double* topk_score, cudaStream_t st) {
+    MAD_PROF("match_simt_kernel", st);
     match_simt_kernel<<<(int)mad_ceil_div(M, TM), 256, 0, st>>>(hi, M, lo, N, hi_n2, lo_n2, cc, mode, row_count, row_offset,
                                                                   pair_hi, pair_lo, pair_score, k, lo_index_base, topk_idx, topk_score);
     MAD_LAUNCH_OK();
@@ -187,7 +190,11 @@ extern "C" int mad_exclusive_scan_i32_to_i64(const int32_t* in, int n, int64_t* 
     MAD_CHECK_ARG(in && out && workspace);
     cub::TransformInputIterator<int64_t, CastI64, const int32_t*> it(in, CastI64());
     size_t b = workspace_bytes;
-    MAD_CUDA(cub::DeviceScan::ExclusiveSum(workspace, b, it, out, n, st));
+    {
+        MAD_PROF("cub_exclusive_sum", st);
+        MAD_CUDA(cub::DeviceScan::ExclusiveSum(workspace, b, it, out, n, st));
+    }
+    MAD_PROF("scan_total_kernel", st);
     scan_total_kernel<<<1, 1, 0, st>>>(in, out, n, total);
     MAD_LAUNCH_OK();
     return MAD_OK;
@@ -198,6 +205,7 @@ extern "C" int mad_topk_merge(const int32_t* idx_in, const double* score_in, int
     MAD_CHECK_ARG(G >= 1 && M >= 0 && k >= 1 && k <= MAD_TOPK_MAX);
     if (M == 0) return MAD_OK;
     MAD_CHECK_ARG(idx_in && score_in && idx_out && score_out);
+    MAD_PROF("topk_merge_kernel", stream);
     topk_merge_kernel<<<(int)mad_ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(idx_in, score_in, G, M, k, idx_out, score_out);
     MAD_LAUNCH_OK();
     return MAD_OK;

@@ -227,6 +227,7 @@ extern "C" int mad_orient(const float* grad4_oct0, const float* grad4_oct1, cons
     const size_t smem = (size_t)n_mask * sizeof(float4);
     if (smem > 200 * 1024) { mad_set_error("mad_orient: patch radius %d too large", r); return MAD_ERR_ARG; }
     MAD_CUDA(cudaFuncSetAttribute(orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    MAD_PROF("orient_kernel", stream);
     orient_kernel<<<n_kp, 128, smem, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, r, mask,
         n_mask, T, r1_table, lim_main, lim_sec, n_ori, slots);
@@ -253,7 +254,11 @@ extern "C" int mad_compact_oriented(const int32_t* n_ori, const int32_t* slots, 
     int* pos = reinterpret_cast<int*>(workspace);
     char* cub_ws = reinterpret_cast<char*>(workspace) + mad_align_up((size_t)n_kp * sizeof(int), 256);
     size_t cub_bytes = workspace_bytes - mad_align_up((size_t)n_kp * sizeof(int), 256);
-    MAD_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, n_ori, pos, n_kp, st));
+    {
+        MAD_PROF("cub_exclusive_sum", st);
+        MAD_CUDA(cub::DeviceScan::ExclusiveSum(cub_ws, cub_bytes, n_ori, pos, n_kp, st));
+    }
+    MAD_PROF("compact_oriented_kernel", st);
     compact_oriented_kernel<<<(int)mad_ceil_div(n_kp, 256), 256, 0, st>>>(n_ori, slots, pos, n_kp, oriented, cap, out_count);
     MAD_LAUNCH_OK();
     return MAD_OK;

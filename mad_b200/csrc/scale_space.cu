@@ -31,6 +31,7 @@ extern "C" int mad_pad3d(const float* in, int nx, int ny, int nz, int pad, float
     MAD_CHECK_ARG(in && out && nx > 0 && ny > 0 && nz > 0 && pad >= 0);
     long long total = (long long)(nx + 2 * pad) * (ny + 2 * pad) * (nz + 2 * pad);
     int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 16);
+    MAD_PROF("pad3d_kernel", stream);
     pad3d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, nx, ny, nz, pad, out, total);
     MAD_LAUNCH_OK();
     return MAD_OK;
@@ -296,6 +297,7 @@ static int upsample_launch(const float* base, int bx, int by, int bz, const Spli
             return MAD_ERR_ARG;
         }
         MAD_CUDA(cudaFuncSetAttribute(spline_up_z_kernel<GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        MAD_PROF("spline_up_z_kernel", st);
         spline_up_z_kernel<GR><<<(unsigned)mad_ceil_div(lines, 32), 32, smem, st>>>(base, wsA, bz, lines, npad, prm);
         MAD_LAUNCH_OK();
     }
@@ -305,6 +307,7 @@ static int upsample_launch(const float* base, int bx, int by, int bz, const Spli
         const long long inner = (long long)by * (2 * bz - 1);
         MAD_CUDA(cudaFuncSetAttribute(spline_up_strided_kernel<double, double, GR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        MAD_PROF("spline_up_x_kernel", st);
         spline_up_strided_kernel<double, double, GR>
             <<<(unsigned)mad_ceil_div(inner, 128), 128, ring_smem, st>>>(wsA, wsB, bx, inner, inner, prm);
         MAD_LAUNCH_OK();
@@ -315,6 +318,7 @@ static int upsample_launch(const float* base, int bx, int by, int bz, const Spli
         const long long lines = (long long)(2 * bx - 1) * inner;
         MAD_CUDA(cudaFuncSetAttribute(spline_up_strided_kernel<double, float, GR>,
                                       cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        MAD_PROF("spline_up_y_kernel", st);
         spline_up_strided_kernel<double, float, GR>
             <<<(unsigned)mad_ceil_div(lines, 128), 128, ring_smem, st>>>(wsB, up, by, inner, lines, prm);
         MAD_LAUNCH_OK();
@@ -538,6 +542,7 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
         const long long inner = (long long)ny * nz;
         const int seg_len = segs_for(inner, nx);
         dim3 grid_dim((unsigned)mad_ceil_div(inner, 128), (unsigned)mad_ceil_div(nx, seg_len));
+        MAD_PROF("log_pass_x_kernel", st);
         log_pass_strided_kernel<R, ACC, 0><<<grid_dim, 128, 0, st>>>(grid, nullptr, P0, Q0, nullptr, nx, inner, inner, seg_len, w);
         MAD_LAUNCH_OK();
     }
@@ -546,6 +551,7 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
         const long long lines = (long long)nx * nz;
         const int seg_len = segs_for(lines, ny);
         dim3 grid_dim((unsigned)mad_ceil_div(lines, 128), (unsigned)mad_ceil_div(ny, seg_len));
+        MAD_PROF("log_pass_y_kernel", st);
         log_pass_strided_kernel<R, ACC, 1><<<grid_dim, 128, 0, st>>>(P0, Q0, P01, Rr, S, ny, inner, lines, seg_len, w);
         MAD_LAUNCH_OK();
     }
@@ -562,6 +568,7 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
             return MAD_ERR_ARG;
         }
         MAD_CUDA(cudaFuncSetAttribute(log_pass_z_kernel<R, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        MAD_PROF("log_pass_z_kernel", st);
         log_pass_z_kernel<R, ACC><<<(unsigned)mad_ceil_div(n_rows, rows), 128, smem, st>>>(P01, Rr, S, log_out, gauss_out, nz, n_rows, rows, rs_in, rs_out, scale, w);
         MAD_LAUNCH_OK();
     }
@@ -631,6 +638,7 @@ extern "C" int mad_gradient(const float* gauss, int nx, int ny, int nz, float* g
     MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad4) & 15) == 0);
     const long long total = (long long)nx * ny * nz;
     const int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 32);
+    MAD_PROF("gradient_kernel", stream);
     gradient_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gauss, nx, ny, nz, reinterpret_cast<float4*>(grad4), total);
     MAD_LAUNCH_OK();
     return MAD_OK;

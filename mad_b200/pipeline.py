@@ -19,11 +19,31 @@ from . import _lib
 from . import tables
 from ._lib import call, KEYPOINT_DTYPE, ORIENTED_DTYPE, MAX_ORI, DSC_LEN
 
-LAUNCHES = {"n": 0}     # kernels launched by this library (bench.py reports it)
-
-
 def _count(n):
-    LAUNCHES["n"] += n
+    pass                # launches are counted inside the library (mad_launch_count)
+
+
+def launch_count():
+    """Kernels launched by libmad_b200 in this process so far."""
+    return int(_lib.lib.mad_launch_count())
+
+
+def profile_enable(on=True):
+    """Per-kernel CUDA-event timing inside the library (measurement only; adds two events per launch)."""
+    call("mad_profile_reset")
+    call("mad_profile_enable", 1 if on else 0)
+
+
+def profile_records():
+    """[(kernel name, milliseconds)] for every launch since profile_enable(True); clears the list."""
+    out = []
+    name = C.c_char_p()
+    ms = C.c_float()
+    for i in range(_lib.lib.mad_profile_count()):
+        call("mad_profile_get", i, C.byref(name), C.byref(ms))
+        out.append((name.value.decode(), float(ms.value)))
+    call("mad_profile_reset")
+    return out
 
 
 def _require_cuda():
