@@ -287,10 +287,11 @@ def describe(space, kp, ori, radius=8):
     return dsc
 
 
-def describe_struct(grid, patch_size=16, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True):
+def describe_struct(grid, patch_size=16, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True,
+                    keep_gauss=False):
     """The whole a1-a12 chain of ``MaD._describe_struct`` (mad/MaD.py:358-368) on device arrays."""
     r = (patch_size - patch_size % 2) // 2
-    sp = build_space(grid, map_padding, sig_init, sig_presmooth, exact_f64=exact_f64, keep_gauss=False)
+    sp = build_space(grid, map_padding, sig_init, sig_presmooth, exact_f64=exact_f64, keep_gauss=keep_gauss)
     kp = detect(sp)
     ori = orient(sp, kp, r)
     dsc = describe(sp, kp, ori, r)
