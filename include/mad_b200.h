@@ -168,14 +168,17 @@ int mad_dsc_norms(const int16_t* dsc, int rows, int32_t* norm2, void* stream);
 int mad_dsc_to_half(const int16_t* dsc, int rows, int rows_padded, void* half_out, void* stream);
 
 /* Threshold mode (the parity contract): all (i, j) with  dot(hi_i, lo_j) / sqrt(n_i n_j) > cc in
- * float64 (integer dot and norms exact); zero rows score 0.  Two passes: COUNT fills
- * row_count[M]; after an exclusive scan into row_offset[M] (mad_exclusive_scan_i32_to_i64), FILL
- * writes pair_hi[..] = i, pair_lo[row_offset[i] + t] (lo ascending) and pair_score -- i.e. the row-major
- * order of np.where(preds > cc).
+ * float64 (integer dot and norms exact); zero rows score 0.
+ * The lo axis is cut into n_seg = mad_match_segments(M, N, impl) contiguous segments (so that a
+ * few hi tiles still fill 148 SMs).  Two passes: COUNT fills seg_count[M][n_seg]; after an
+ * exclusive scan over that array in memory order (mad_exclusive_scan_i32_to_i64, n = M*n_seg)
+ * FILL writes pair_hi / pair_lo / pair_score starting at seg_offset[i][s], lo ascending -- i.e. the
+ * row-major order of np.where(preds > cc) (mad/MaD.py:423-424).
  * impl: 0 = tcgen05 tensor-core kernel (product), 1 = SIMT integer kernel (device-side check). */
-int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int32_t* row_count, int impl,
+int mad_match_segments(int M, int N, int impl);
+int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, int32_t* seg_count, int impl,
                     void* stream);
-int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double cc, const int64_t* row_offset,
+int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, const int64_t* seg_offset,
                    int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int impl, void* stream);
 size_t mad_exclusive_scan_workspace_bytes(int n);
 int mad_exclusive_scan_i32_to_i64(const int32_t* in, int n, int64_t* out, int64_t* total,
@@ -183,9 +186,12 @@ int mad_exclusive_scan_i32_to_i64(const int32_t* in, int n, int64_t* out, int64_
 
 /* Top-k mode (extension): per hi row the k best lo rows by (score desc, index asc);
  * lo_index_base is added to the stored indices (sharded reference axis).  k <= 32.
- * topk_idx[M][k] (-1 padded), topk_score[M][k] float64 (-inf padded). */
+ * topk_idx[M][k] (-1 padded), topk_score[M][k] float64 (-inf padded).  Workspace: per-segment
+ * partial lists (mad_match_topk_workspace_bytes). */
+size_t mad_match_topk_workspace_bytes(int M, int N, int k, int impl);
 int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, int lo_index_base,
-                   int32_t* topk_idx, double* topk_score, int impl, void* stream);
+                   int32_t* topk_idx, double* topk_score, void* workspace, size_t workspace_bytes,
+                   int impl, void* stream);
 /* Merges G per-shard top-k lists [G][M][k] into one [M][k] with the same ordering rule. */
 int mad_topk_merge(const int32_t* idx_in, const double* score_in, int G, int M, int k,
                    int32_t* idx_out, double* score_out, void* stream);

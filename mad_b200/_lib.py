@@ -71,11 +71,13 @@ SIGNATURES = {
     "mad_describe": (_I, [_P, _P, _P, _P, _P, _I, _I, C.POINTER(MadZoneTable), _P, _P, _I, _P, _P]),
     "mad_dsc_norms": (_I, [_P, _I, _P, _P]),
     "mad_dsc_to_half": (_I, [_P, _I, _I, _P, _P]),
-    "mad_match_count": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), C.c_double, _P, _I, _P]),
-    "mad_match_fill": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), C.c_double, _P, _P, _P, _P, _I, _P]),
+    "mad_match_segments": (_I, [_I, _I, _I]),
+    "mad_match_count": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), C.c_double, _I, _P, _I, _P]),
+    "mad_match_fill": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), C.c_double, _I, _P, _P, _P, _P, _I, _P]),
     "mad_exclusive_scan_workspace_bytes": (_SZ, [_I]),
     "mad_exclusive_scan_i32_to_i64": (_I, [_P, _I, _P, _P, _P, _SZ, _P]),
-    "mad_match_topk": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), _I, _I, _P, _P, _I, _P]),
+    "mad_match_topk_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
+    "mad_match_topk": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), _I, _I, _P, _P, _P, _SZ, _I, _P]),
     "mad_topk_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
 }
 

@@ -109,45 +109,86 @@ static int check_sets(const MadDscSet* hi, const MadDscSet* lo, int impl) {
     return MAD_OK;
 }
 
-static int run_match(const MadDscSet* hi, const MadDscSet* lo, double cc, int mode, int32_t* row_count,
-                     const int64_t* row_offset, int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int k, int base,
+static int run_match(const MadDscSet* hi, const MadDscSet* lo, double cc, int mode, int S, int32_t* seg_count,
+                     const int64_t* seg_offset, int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int k, int base,
                      int32_t* topk_idx, double* topk_score, int impl, cudaStream_t st) {
     if (impl == 1)
-        return mad_match_simt(hi->dsc, hi->rows, lo->dsc, lo->rows, hi->norm2, lo->norm2, cc, mode, row_count, row_offset,
+        return mad_match_simt(hi->dsc, hi->rows, lo->dsc, lo->rows, hi->norm2, lo->norm2, cc, mode, S, seg_count, seg_offset,
                               pair_hi, pair_lo, pair_score, k, base, topk_idx, topk_score, st);
     return mad_match_tc(hi->half, hi->rows, hi->rows_padded, lo->half, lo->rows, lo->rows_padded, hi->norm2, lo->norm2, cc,
-                        mode, row_count, row_offset, pair_hi, pair_lo, pair_score, k, base, topk_idx, topk_score, st);
+                        mode, S, seg_count, seg_offset, pair_hi, pair_lo, pair_score, k, base, topk_idx, topk_score, st);
 }
 
-extern "C" int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int32_t* row_count, int impl,
-                               void* stream) {
+// Segment count: the tcgen05 kernel's choice for both implementations (same output layout).
+extern "C" int mad_match_segments(int M, int N, int impl) {
+    (void)impl;
+    return mad_match_tc_segments(M, N);
+}
+
+static int check_segments(const MadDscSet* hi, const MadDscSet* lo, int n_seg) {
+    const int n_tiles = (int)mad_ceil_div(lo->rows, MAD_MATCH_SEG_TILE);
+    MAD_CHECK_ARG(n_seg >= 1 && n_seg <= (n_tiles > 0 ? n_tiles : 1));
+    (void)hi;
+    return MAD_OK;
+}
+
+extern "C" int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, int32_t* seg_count,
+                               int impl, void* stream) {
     int rc = check_sets(hi, lo, impl);
     if (rc != MAD_OK) return rc;
     if (hi->rows == 0) return MAD_OK;
-    MAD_CHECK_ARG(row_count);
+    MAD_CHECK_ARG(seg_count && n_seg >= 1);
     if (lo->rows == 0) {
-        MAD_CUDA(cudaMemsetAsync(row_count, 0, sizeof(int32_t) * hi->rows, (cudaStream_t)stream));
+        MAD_CUDA(cudaMemsetAsync(seg_count, 0, sizeof(int32_t) * (size_t)hi->rows * n_seg, (cudaStream_t)stream));
         return MAD_OK;
     }
-    return run_match(hi, lo, cc, 0, row_count, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, impl, (cudaStream_t)stream);
+    rc = check_segments(hi, lo, n_seg);
+    if (rc != MAD_OK) return rc;
+    return run_match(hi, lo, cc, 0, n_seg, seg_count, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr, nullptr, impl,
+                     (cudaStream_t)stream);
 }
 
-extern "C" int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double cc, const int64_t* row_offset,
+extern "C" int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, const int64_t* seg_offset,
                               int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int impl, void* stream) {
     int rc = check_sets(hi, lo, impl);
     if (rc != MAD_OK) return rc;
     if (hi->rows == 0 || lo->rows == 0) return MAD_OK;
-    MAD_CHECK_ARG(row_offset && pair_hi && pair_lo && pair_score);
-    return run_match(hi, lo, cc, 1, nullptr, row_offset, pair_hi, pair_lo, pair_score, 0, 0, nullptr, nullptr, impl, (cudaStream_t)stream);
+    MAD_CHECK_ARG(seg_offset && pair_hi && pair_lo && pair_score);
+    rc = check_segments(hi, lo, n_seg);
+    if (rc != MAD_OK) return rc;
+    return run_match(hi, lo, cc, 1, n_seg, nullptr, seg_offset, pair_hi, pair_lo, pair_score, 0, 0, nullptr, nullptr, impl,
+                     (cudaStream_t)stream);
+}
+
+extern "C" size_t mad_match_topk_workspace_bytes(int M, int N, int k, int impl) {
+    const int S = mad_match_segments(M, N, impl);
+    if (S <= 1 || M <= 0) return 256;
+    return mad_align_up((size_t)S * M * k * sizeof(int32_t), 256) + mad_align_up((size_t)S * M * k * sizeof(double), 256);
 }
 
 extern "C" int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, int lo_index_base, int32_t* topk_idx,
-                              double* topk_score, int impl, void* stream) {
+                              double* topk_score, void* workspace, size_t workspace_bytes, int impl, void* stream) {
     int rc = check_sets(hi, lo, impl);
     if (rc != MAD_OK) return rc;
     MAD_CHECK_ARG(k >= 1 && k <= MAD_TOPK_MAX);
     if (hi->rows == 0) return MAD_OK;
     MAD_CHECK_ARG(topk_idx && topk_score);
-    return run_match(hi, lo, 0.0, 2, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, topk_idx, topk_score, impl,
-                     (cudaStream_t)stream);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int M = hi->rows;
+    if (lo->rows == 0) {            // nothing to match: -1 / -inf padding
+        MAD_CUDA(cudaMemsetAsync(topk_idx, 0xFF, sizeof(int32_t) * (size_t)M * k, st));
+        // -inf as float64 = 0xFFF0000000000000: written by the merge kernel over zero shards
+        return mad_topk_merge_launch(topk_idx, topk_score, 0, M, k, topk_idx, topk_score, st);
+    }
+    const int S = mad_match_segments(M, lo->rows, impl);
+    if (S == 1)
+        return run_match(hi, lo, 0.0, 2, 1, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, topk_idx, topk_score,
+                         impl, st);
+    MAD_CHECK_ARG(workspace && workspace_bytes >= mad_match_topk_workspace_bytes(M, lo->rows, k, impl));
+    int32_t* pidx = reinterpret_cast<int32_t*>(workspace);
+    double* pscore = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) +
+                                               mad_align_up((size_t)S * M * k * sizeof(int32_t), 256));
+    rc = run_match(hi, lo, 0.0, 2, S, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, pidx, pscore, impl, st);
+    if (rc != MAD_OK) return rc;
+    return mad_topk_merge_launch(pidx, pscore, S, M, k, topk_idx, topk_score, st);
 }

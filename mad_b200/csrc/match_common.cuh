@@ -28,12 +28,18 @@ __host__ __device__ __forceinline__ void mad_topk_insert(double* bs, int* bi, in
     bi[q] = id;
 }
 
+// Both kernels cut the lo axis into S segments of `tiles_per_seg` 256-column tiles.
+#define MAD_MATCH_SEG_TILE 256
+
 int mad_match_simt(const int16_t* hi, int M, const int16_t* lo, int N, const int32_t* hi_n2, const int32_t* lo_n2,
-                   double cc, int mode, int32_t* row_count, const int64_t* row_offset, int32_t* pair_hi,
+                   double cc, int mode, int S, int32_t* seg_count, const int64_t* seg_offset, int32_t* pair_hi,
                    int32_t* pair_lo, double* pair_score, int k, int lo_index_base, int32_t* topk_idx,
                    double* topk_score, cudaStream_t st);
 
+int mad_match_tc_segments(int M, int N);
 int mad_match_tc(const void* hi_half, int M, int M_pad, const void* lo_half, int N, int N_pad,
-                 const int32_t* hi_n2, const int32_t* lo_n2, double cc, int mode, int32_t* row_count,
-                 const int64_t* row_offset, int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int k,
+                 const int32_t* hi_n2, const int32_t* lo_n2, double cc, int mode, int S, int32_t* seg_count,
+                 const int64_t* seg_offset, int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int k,
                  int lo_index_base, int32_t* topk_idx, double* topk_score, cudaStream_t st);
+int mad_topk_merge_launch(const int32_t* idx_in, const double* score_in, int G, int M, int k, int32_t* idx_out,
+                          double* score_out, cudaStream_t st);

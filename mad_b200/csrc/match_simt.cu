@@ -41,7 +41,7 @@ constexpr int TM = 64, TN = 64, TK = 64;
 __global__ void __launch_bounds__(256)
 match_simt_kernel(const int16_t* __restrict__ hi, int M, const int16_t* __restrict__ lo, int N,
                   const int32_t* __restrict__ hi_n2, const int32_t* __restrict__ lo_n2, double cc, int mode,
-                  int32_t* __restrict__ row_count, const int64_t* __restrict__ row_offset,
+                  int S, int cols_per_seg, int32_t* __restrict__ row_count, const int64_t* __restrict__ row_offset,
                   int32_t* __restrict__ pair_hi, int32_t* __restrict__ pair_lo, double* __restrict__ pair_score,
                   int k, int lo_index_base, int32_t* __restrict__ topk_idx, double* __restrict__ topk_score) {
     __shared__ int16_t sa[TM][TK + 2];
@@ -49,6 +49,9 @@ match_simt_kernel(const int16_t* __restrict__ hi, int M, const int16_t* __restri
     __shared__ int dots[TM][TN + 1];
     const int tid = threadIdx.x;
     const int m0 = blockIdx.x * TM;
+    const int seg = blockIdx.y;
+    const int n_begin = seg * cols_per_seg;
+    const int n_end = min(N, n_begin + cols_per_seg);
     const int ty = tid / 16, tx = tid % 16;   // 16x16 threads, 4x4 outputs each
 
     // per-row running state (threads 0..63 own one row each)
@@ -58,10 +61,10 @@ match_simt_kernel(const int16_t* __restrict__ hi, int M, const int16_t* __restri
     double bs[MAD_TOPK_MAX];
     int bi[MAD_TOPK_MAX];
     if (mode == 2) for (int q = 0; q < MAD_TOPK_MAX; ++q) { bs[q] = -INFINITY; bi[q] = -1; }
-    if (mode == 1 && tid < TM && my_row < M) wpos = row_offset[my_row];
+    if (mode == 1 && tid < TM && my_row < M) wpos = row_offset[(long long)my_row * S + seg];
     const double my_n2 = (tid < TM && my_row < M) ? (double)hi_n2[my_row] : 0.0;
 
-    for (int n0 = 0; n0 < N; n0 += TN) {
+    for (int n0 = n_begin; n0 < n_end; n0 += TN) {
         int acc[4][4];
 #pragma unroll
         for (int a = 0; a < 4; ++a)
@@ -71,7 +74,7 @@ match_simt_kernel(const int16_t* __restrict__ hi, int M, const int16_t* __restri
             for (int q = tid; q < TM * TK; q += 256) {
                 const int r = q / TK, c = q % TK;
                 sa[r][c] = (m0 + r < M) ? hi[(long long)(m0 + r) * MAD_DSC_LEN + k0 + c] : (int16_t)0;
-                sb[r][c] = (n0 + r < N) ? lo[(long long)(n0 + r) * MAD_DSC_LEN + k0 + c] : (int16_t)0;
+                sb[r][c] = (n0 + r < n_end) ? lo[(long long)(n0 + r) * MAD_DSC_LEN + k0 + c] : (int16_t)0;
             }
             __syncthreads();
 #pragma unroll 8
@@ -94,7 +97,7 @@ match_simt_kernel(const int16_t* __restrict__ hi, int M, const int16_t* __restri
             for (int b = 0; b < 4; ++b) dots[ty * 4 + a][tx * 4 + b] = acc[a][b];
         __syncthreads();
         if (tid < TM && my_row < M) {
-            for (int j = 0; j < TN && n0 + j < N; ++j) {
+            for (int j = 0; j < TN && n0 + j < n_end; ++j) {
                 const double s = mad_score(dots[tid][j], my_n2, (double)lo_n2[n0 + j]);
                 if (mode == 2) {
                     mad_topk_insert(bs, bi, k, s, lo_index_base + n0 + j);
@@ -107,9 +110,13 @@ match_simt_kernel(const int16_t* __restrict__ hi, int M, const int16_t* __restri
         __syncthreads();
     }
     if (tid < TM && my_row < M) {
-        if (mode == 0) row_count[my_row] = cnt;
+        if (mode == 0) row_count[(long long)my_row * S + seg] = cnt;
         if (mode == 2)
-            for (int q = 0; q < k; ++q) { topk_idx[(long long)my_row * k + q] = bi[q]; topk_score[(long long)my_row * k + q] = bs[q]; }
+            for (int q = 0; q < k; ++q) {
+                const long long o = ((long long)seg * M + my_row) * k + q;
+                topk_idx[o] = bi[q];
+                topk_score[o] = bs[q];
+            }
     }
 }
 
@@ -162,12 +169,15 @@ extern "C" int mad_dsc_to_half(const int16_t* dsc, int rows, int rows_padded, vo
 }
 
 int mad_match_simt(const int16_t* hi, int M, const int16_t* lo, int N, const int32_t* hi_n2, const int32_t* lo_n2,
-                   double cc, int mode, int32_t* row_count, const int64_t* row_offset, int32_t* pair_hi,
+                   double cc, int mode, int S, int32_t* seg_count, const int64_t* seg_offset, int32_t* pair_hi,
                    int32_t* pair_lo, double* pair_score, int k, int lo_index_base, int32_t* topk_idx,
                    double* topk_score, cudaStream_t st) {
+    const int n_tiles = (int)mad_ceil_div(N, MAD_MATCH_SEG_TILE);
+    const int cols_per_seg = (int)mad_ceil_div(n_tiles, S) * MAD_MATCH_SEG_TILE;
+    dim3 grid((unsigned)mad_ceil_div(M, TM), (unsigned)S);
     MAD_PROF("match_simt_kernel", st);
-    match_simt_kernel<<<(int)mad_ceil_div(M, TM), 256, 0, st>>>(hi, M, lo, N, hi_n2, lo_n2, cc, mode, row_count, row_offset,
-                                                                  pair_hi, pair_lo, pair_score, k, lo_index_base, topk_idx, topk_score);
+    match_simt_kernel<<<grid, 256, 0, st>>>(hi, M, lo, N, hi_n2, lo_n2, cc, mode, S, cols_per_seg, seg_count, seg_offset,
+                                            pair_hi, pair_lo, pair_score, k, lo_index_base, topk_idx, topk_score);
     MAD_LAUNCH_OK();
     return MAD_OK;
 }
@@ -200,13 +210,18 @@ extern "C" int mad_exclusive_scan_i32_to_i64(const int32_t* in, int n, int64_t* 
     return MAD_OK;
 }
 
+int mad_topk_merge_launch(const int32_t* idx_in, const double* score_in, int G, int M, int k, int32_t* idx_out,
+                          double* score_out, cudaStream_t st) {
+    MAD_PROF("topk_merge_kernel", st);
+    topk_merge_kernel<<<(int)mad_ceil_div(M, 128), 128, 0, st>>>(idx_in, score_in, G, M, k, idx_out, score_out);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}
+
 extern "C" int mad_topk_merge(const int32_t* idx_in, const double* score_in, int G, int M, int k, int32_t* idx_out,
                               double* score_out, void* stream) {
     MAD_CHECK_ARG(G >= 1 && M >= 0 && k >= 1 && k <= MAD_TOPK_MAX);
     if (M == 0) return MAD_OK;
     MAD_CHECK_ARG(idx_in && score_in && idx_out && score_out);
-    MAD_PROF("topk_merge_kernel", stream);
-    topk_merge_kernel<<<(int)mad_ceil_div(M, 128), 128, 0, (cudaStream_t)stream>>>(idx_in, score_in, G, M, k, idx_out, score_out);
-    MAD_LAUNCH_OK();
-    return MAD_OK;
+    return mad_topk_merge_launch(idx_in, score_in, G, M, k, idx_out, score_out, (cudaStream_t)stream);
 }

@@ -19,10 +19,6 @@ from . import _lib
 from . import tables
 from ._lib import call, KEYPOINT_DTYPE, ORIENTED_DTYPE, MAX_ORI, DSC_LEN
 
-def _count(n):
-    pass                # launches are counted inside the library (mad_launch_count)
-
-
 def launch_count():
     """Kernels launched by libmad_b200 in this process so far."""
     return int(_lib.lib.mad_launch_count())
@@ -129,7 +125,6 @@ def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True
         bx, by, bz = nx + 2 * map_padding, ny + 2 * map_padding, nz + 2 * map_padding
         base = torch.empty((bx, by, bz), dtype=torch.float32, device=dev)
         call("mad_pad3d", _ptr(grid), nx, ny, nz, int(map_padding), _ptr(base), st)
-        _count(1)
     else:
         bx, by, bz = nx, ny, nz
         base = grid
@@ -144,7 +139,6 @@ def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True
         call("mad_upsample_presmooth", _ptr(base), bx, by, bz, _dptr(gw), rad, _ptr(up), _ptr(ws), ws_bytes, st)
     else:
         call("mad_upsample_presmooth", _ptr(base), bx, by, bz, C.c_void_p(0), 0, _ptr(up), _ptr(ws), ws_bytes, st)
-    _count(3)
     del ws
     sp.grids = [up, base]
     sp.dims = [(ux, uy, uz), (bx, by, bz)]
@@ -163,7 +157,6 @@ def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True
         del ws
         gr = torch.empty((gx, gy, gz, 4), dtype=torch.float32, device=dev)
         call("mad_gradient", _ptr(gs), gx, gy, gz, _ptr(gr), st)
-        _count(4)
         sp.logs.append(lg)
         sp.gauss.append(gs if keep_gauss else None)
         sp.grad4.append(gr)
@@ -208,7 +201,6 @@ def detect(space, border=12, threshold=5e-2, cap=None):
         for o, (lg, (gx, gy, gz)) in enumerate(zip(space.logs, space.dims)):
             call("mad_detect", _ptr(lg), gx, gy, gz, o, int(border), C.c_float(threshold), _ptr(cand), cap,
                  _ptr(counter), st)
-            _count(1)
         n = int(counter.item())
         if n <= cap:
             break
@@ -219,7 +211,6 @@ def detect(space, border=12, threshold=5e-2, cap=None):
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     dims = space.dims_host
     call("mad_sort_keypoints", _ptr(cand), n, _dptr(dims), _ptr(out), _ptr(out_count), _ptr(ws), ws_bytes, st)
-    _count(5)
     return Keypoints(out, out_count.item())
 
 
@@ -266,7 +257,6 @@ def orient(space, kp, radius=8, lim_main=6, lim_sec=6):
     ws_bytes = _lib.lib.mad_compact_oriented_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     call("mad_compact_oriented", _ptr(n_ori), _ptr(slots), n, _ptr(out), cap, _ptr(out_count), _ptr(ws), ws_bytes, st)
-    _count(3)
     return Oriented(out, out_count.item())
 
 
@@ -283,7 +273,6 @@ def describe(space, kp, ori, radius=8):
     dims = space.dims_host
     call("mad_describe", _ptr(space.grad4[0]), _ptr(space.grad4[1]), _dptr(dims), _ptr(kp.table), _ptr(ori.table), d,
          int(radius), C.byref(tb.z_dsc), _ptr(tb.rf), _ptr(tb.rf_inv), tb.ori_zones, _ptr(dsc), st)
-    _count(1)
     return dsc
 
 
@@ -316,12 +305,10 @@ class DescriptorSet(object):
         self.rows_padded = (self.rows + 127) // 128 * 128
         self.norm2 = torch.empty(max(self.rows, 1), dtype=torch.int32, device=dev)
         call("mad_dsc_norms", _ptr(self.dsc), self.rows, _ptr(self.norm2), st)
-        _count(1)
         self.half = None
         if need_half:
             self.half = torch.empty((max(self.rows_padded, 128), DSC_LEN), dtype=torch.float16, device=dev)
             call("mad_dsc_to_half", _ptr(self.dsc), self.rows, self.rows_padded, _ptr(self.half), st)
-            _count(1)
         s = _lib.MadDscSet()
         s.dsc = self.dsc.data_ptr()
         s.half = self.half.data_ptr() if self.half is not None else 0
@@ -344,20 +331,20 @@ def match_threshold(hi, lo, cc=0.6, impl=0):
     if m == 0 or lo.rows == 0:
         e = torch.empty(0, dtype=torch.int32, device=dev)
         return e, e.clone(), torch.empty(0, dtype=torch.float64, device=dev)
-    row_count = torch.empty(m, dtype=torch.int32, device=dev)
-    call("mad_match_count", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), _ptr(row_count), impl, st)
-    row_off = torch.empty(m, dtype=torch.int64, device=dev)
+    n_seg = int(_lib.lib.mad_match_segments(m, lo.rows, impl))
+    seg_count = torch.empty(m * n_seg, dtype=torch.int32, device=dev)
+    call("mad_match_count", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), n_seg, _ptr(seg_count), impl, st)
+    seg_off = torch.empty(m * n_seg, dtype=torch.int64, device=dev)
     total = torch.zeros(1, dtype=torch.int64, device=dev)
-    ws_bytes = _lib.lib.mad_exclusive_scan_workspace_bytes(m)
+    ws_bytes = _lib.lib.mad_exclusive_scan_workspace_bytes(m * n_seg)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    call("mad_exclusive_scan_i32_to_i64", _ptr(row_count), m, _ptr(row_off), _ptr(total), _ptr(ws), ws_bytes, st)
+    call("mad_exclusive_scan_i32_to_i64", _ptr(seg_count), m * n_seg, _ptr(seg_off), _ptr(total), _ptr(ws), ws_bytes, st)
     p = int(total.item())
     pair_hi = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
     pair_lo = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
     score = torch.empty(max(p, 1), dtype=torch.float64, device=dev)
-    call("mad_match_fill", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), _ptr(row_off), _ptr(pair_hi), _ptr(pair_lo),
+    call("mad_match_fill", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), n_seg, _ptr(seg_off), _ptr(pair_hi), _ptr(pair_lo),
          _ptr(score), impl, st)
-    _count(4)
     return pair_hi[:p], pair_lo[:p], score[:p]
 
 
@@ -368,8 +355,10 @@ def match_topk(hi, lo, k=8, lo_index_base=0, impl=0):
     st = _stream()
     idx = torch.empty((hi.rows, k), dtype=torch.int32, device=dev)
     score = torch.empty((hi.rows, k), dtype=torch.float64, device=dev)
-    call("mad_match_topk", C.byref(hi.c), C.byref(lo.c), int(k), int(lo_index_base), _ptr(idx), _ptr(score), impl, st)
-    _count(1)
+    ws_bytes = _lib.lib.mad_match_topk_workspace_bytes(hi.rows, lo.rows, int(k), impl)
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    call("mad_match_topk", C.byref(hi.c), C.byref(lo.c), int(k), int(lo_index_base), _ptr(idx), _ptr(score), _ptr(ws),
+         ws_bytes, impl, st)
     return idx, score
 
 
@@ -380,5 +369,4 @@ def topk_merge(idx_g, score_g):
     idx = torch.empty((m, k), dtype=torch.int32, device=dev)
     score = torch.empty((m, k), dtype=torch.float64, device=dev)
     call("mad_topk_merge", _ptr(idx_g.contiguous()), _ptr(score_g.contiguous()), g, m, k, _ptr(idx), _ptr(score), _stream())
-    _count(1)
     return idx, score

@@ -110,19 +110,55 @@ def fit_to_cube(grid, n):
     return out
 
 
-def assembly_map(n, resolution, voxelsp, n_sub, atoms_per_sub, seed0):
-    """C2/C3-style map: ``n_sub`` random-walk subunits packed on a coarse lattice inside an
-    n^3 box of ``voxelsp`` A voxels, simulated at ``resolution`` A and fitted to exactly n^3."""
+def assembly_atoms(n, voxelsp, n_sub, atoms_per_sub, seed0, box=None):
+    """Atom sets of ``n_sub`` random-walk subunits packed on a coarse lattice inside an n^3 box of
+    ``voxelsp`` A voxels (list of [atoms,3] arrays, one per subunit; seeds seed0 .. seed0+n_sub-1)."""
     side = n * voxelsp
     per_axis = int(math.ceil(n_sub ** (1.0 / 3.0)))
     cell = side * 0.8 / per_axis
+    if box is None:
+        box = cell * 0.92
     pts = []
     for s in range(n_sub):
         ix, iy, iz = s % per_axis, (s // per_axis) % per_axis, s // (per_axis * per_axis)
         org = (0.1 * side + ix * cell, 0.1 * side + iy * cell, 0.1 * side + iz * cell)
-        pts.append(random_walk_atoms(atoms_per_sub, cell * 0.92, seed0 + s, origin=org))
+        pts.append(random_walk_atoms(atoms_per_sub, min(box, cell * 0.92), seed0 + s, origin=org))
+    return pts
+
+
+def assembly_map(n, resolution, voxelsp, n_sub, atoms_per_sub, seed0, box=None):
+    """C2/C3-style map: the subunits of ``assembly_atoms`` simulated together at ``resolution`` A
+    and fitted to exactly n^3."""
+    pts = assembly_atoms(n, voxelsp, n_sub, atoms_per_sub, seed0, box)
     grid, _ = simulate_density(np.concatenate(pts), resolution, voxelsp)
     return fit_to_cube(grid, n)
+
+
+def assembly_with_components(n, resolution, voxelsp, n_sub, atoms_per_sub, seed0, box=None):
+    """(assembly map n^3, [component maps]) -- each component simulated alone from its own atoms
+    (what MaD does with the subunit PDBs, mad/MapSpace.py:73-76), origin dropped."""
+    pts = assembly_atoms(n, voxelsp, n_sub, atoms_per_sub, seed0, box)
+    grid, _ = simulate_density(np.concatenate(pts), resolution, voxelsp)
+    comps = [simulate_density(p, resolution, voxelsp)[0] for p in pts]
+    return fit_to_cube(grid, n), comps
+
+
+def representative_crop(grid, side, level=0.05, step=None):
+    """Sub-cube of ``side``^3 whose occupancy (fraction of voxels > level) is closest to the whole
+    map's: the bounded CPU sample of a benchmark-sized map (same voxels/s definition)."""
+    n = grid.shape
+    step = step or max(side // 2, 1)
+    occ = grid > level
+    target = float(occ.mean())
+    best, best_err = (0, 0, 0), None
+    for x in range(0, max(n[0] - side, 0) + 1, step):
+        for y in range(0, max(n[1] - side, 0) + 1, step):
+            for z in range(0, max(n[2] - side, 0) + 1, step):
+                f = float(occ[x:x + side, y:y + side, z:z + side].mean())
+                if best_err is None or abs(f - target) < best_err:
+                    best, best_err = (x, y, z), abs(f - target)
+    x, y, z = best
+    return np.ascontiguousarray(grid[x:x + side, y:y + side, z:z + side]), best
 
 
 def synthetic_descriptors(m, seed, noisy_copy_of=None, copy_frac=0.5, redraw=0.10):

@@ -45,7 +45,7 @@ def test_bad_arguments_are_rejected_without_touching_the_device(lib):
     assert b"bad argument" in L.mad_last_error_string()
     assert L.mad_upsample_presmooth(None, 8, 8, 8, None, 0, None, None, 0, None) == -1
     assert L.mad_log_gauss(None, 8, 8, 8, None, None, 8, 4.0, None, None, None, 0, 1, None) == -1
-    assert L.mad_match_topk(None, None, 8, 0, None, None, 0, None) == -1
+    assert L.mad_match_topk(None, None, 8, 0, None, None, None, 0, 0, None) == -1
     assert L.mad_topk_merge(None, None, 0, 1, 8, None, None, None) == -1
     with pytest.raises(lib.MadError):
         lib.call("mad_gradient", None, 1, 1, 1, None, None)
