@@ -153,17 +153,27 @@ int mad_describe(const float* grad4_oct0, const float* grad4_oct1, const int* di
 
 /* ---- a15: descriptor matching (mad/MaD.py:416-424) ---------------------------------------------- */
 /* A descriptor set prepared for matching (device pointers; the struct itself lives on the host).
- * norm2: exact integer squared L2 norms.  half: fp16 copy [rows_padded][1024] (zero rows beyond
- * `rows`, rows_padded a multiple of 128) -- the tensor-core operand; exact because descriptor
- * entries are integers <= 2048.  dsc is only read by the SIMT check kernel (impl = 1). */
+ * norm2: exact integer squared L2 norms.  u8: uint8 copy [rows_padded][1024] (zero rows beyond
+ * `rows`, rows_padded a multiple of 128) -- the operand of the tcgen05 kind::i8 kernel, exact while
+ * max_entry <= 255 (true for every patch size <= 24: an entry counts the votes of one sub-block).
+ * rnorm: float 1/sqrt(norm2) per padded row (0 for zero rows), the fp32 pre-filter's scale.
+ * half: optional fp16 copy for the general tensor-core kernel (impl = 2, entries <= 2048).
+ * dsc is only read by the SIMT check kernel (impl = 1). */
 typedef struct MadDscSet {
     const int16_t* dsc;   /* [rows][1024] */
-    const void* half;     /* [rows_padded][1024] fp16 */
+    const void* half;     /* [rows_padded][1024] fp16, or NULL */
     const int32_t* norm2; /* [rows] */
+    const uint8_t* u8;    /* [rows_padded][1024], or NULL */
+    const float* rnorm;   /* [rows_padded], or NULL */
     int32_t rows;
     int32_t rows_padded;
+    int32_t max_entry;    /* largest descriptor entry (host copy of what mad_dsc_prepare found) */
 } MadDscSet;
 
+/* Fills norm2[rows], rnorm[rows_padded], u8[rows_padded][1024] (may be NULL) and atomically
+ * raises *max_entry (device int32, caller zeroes it) to the largest entry seen. */
+int mad_dsc_prepare(const int16_t* dsc, int rows, int rows_padded, int32_t* norm2, float* rnorm,
+                    uint8_t* u8, int32_t* max_entry, void* stream);
 int mad_dsc_norms(const int16_t* dsc, int rows, int32_t* norm2, void* stream);
 int mad_dsc_to_half(const int16_t* dsc, int rows, int rows_padded, void* half_out, void* stream);
 
@@ -174,7 +184,9 @@ int mad_dsc_to_half(const int16_t* dsc, int rows, int rows_padded, void* half_ou
  * exclusive scan over that array in memory order (mad_exclusive_scan_i32_to_i64, n = M*n_seg)
  * FILL writes pair_hi / pair_lo / pair_score starting at seg_offset[i][s], lo ascending -- i.e. the
  * row-major order of np.where(preds > cc) (mad/MaD.py:423-424).
- * impl: 0 = tcgen05 tensor-core kernel (product), 1 = SIMT integer kernel (device-side check). */
+ * impl: 1 = SIMT integer kernel (device-side check), 2 = fp16 tcgen05 kernel (entries <= 2048).
+ * The product path for threshold matching is the ONE-pass mad_match_pairs below (impl 0 here is
+ * accepted as an alias of 2). */
 int mad_match_segments(int M, int N, int impl);
 int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, int32_t* seg_count, int impl,
                     void* stream);
@@ -184,10 +196,24 @@ size_t mad_exclusive_scan_workspace_bytes(int n);
 int mad_exclusive_scan_i32_to_i64(const int32_t* in, int n, int64_t* out, int64_t* total,
                                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* One-pass threshold matching on the uint8 tcgen05 kernel (the product path): every pair with
+ * cosine > cc is appended, unordered, to cand_key[] = (hi << 32) | lo and cand_dot[] = exact integer
+ * dot product; *count (device, reset by the call) receives the number of pairs FOUND, which may
+ * exceed cap -- then only cap were stored and the caller repeats with a larger buffer.
+ * mad_match_pairs_finish sorts the n stored candidates by (hi, lo) -- the row-major order of
+ * np.where(preds > cc), mad/MaD.py:423-424 -- and evaluates the float64 scores. */
+int mad_match_pairs(const MadDscSet* hi, const MadDscSet* lo, double cc, uint64_t* cand_key, int32_t* cand_dot,
+                    uint64_t cap, uint64_t* count, void* stream);
+size_t mad_match_pairs_finish_workspace_bytes(long long n);
+int mad_match_pairs_finish(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows,
+                           const int32_t* hi_n2, const int32_t* lo_n2, int32_t* pair_hi, int32_t* pair_lo,
+                           double* pair_score, void* workspace, size_t workspace_bytes, void* stream);
+
 /* Top-k mode (extension): per hi row the k best lo rows by (score desc, index asc);
  * lo_index_base is added to the stored indices (sharded reference axis).  k <= 32.
  * topk_idx[M][k] (-1 padded), topk_score[M][k] float64 (-inf padded).  Workspace: per-segment
- * partial lists (mad_match_topk_workspace_bytes). */
+ * partial lists (mad_match_topk_workspace_bytes).  impl: 0 = uint8 tcgen05 kernel (product; needs
+ * max_entry <= 255), 1 = SIMT check kernel, 2 = fp16 tcgen05 kernel. */
 size_t mad_match_topk_workspace_bytes(int M, int N, int k, int impl);
 int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, int lo_index_base,
                    int32_t* topk_idx, double* topk_score, void* workspace, size_t workspace_bytes,

@@ -38,8 +38,8 @@ class MadZoneTable(C.Structure):
 
 
 class MadDscSet(C.Structure):
-    _fields_ = [("dsc", C.c_void_p), ("half", C.c_void_p), ("norm2", C.c_void_p),
-                ("rows", C.c_int32), ("rows_padded", C.c_int32)]
+    _fields_ = [("dsc", C.c_void_p), ("half", C.c_void_p), ("norm2", C.c_void_p), ("u8", C.c_void_p),
+                ("rnorm", C.c_void_p), ("rows", C.c_int32), ("rows_padded", C.c_int32), ("max_entry", C.c_int32)]
 
 
 _P = C.c_void_p
@@ -69,6 +69,10 @@ SIGNATURES = {
     "mad_compact_oriented_workspace_bytes": (_SZ, [_I]),
     "mad_compact_oriented": (_I, [_P, _P, _I, _P, _I, _P, _P, _SZ, _P]),
     "mad_describe": (_I, [_P, _P, _P, _P, _P, _I, _I, C.POINTER(MadZoneTable), _P, _P, _I, _P, _P]),
+    "mad_dsc_prepare": (_I, [_P, _I, _I, _P, _P, _P, _P, _P]),
+    "mad_match_pairs": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), C.c_double, _P, _P, C.c_uint64, _P, _P]),
+    "mad_match_pairs_finish_workspace_bytes": (_SZ, [C.c_longlong]),
+    "mad_match_pairs_finish": (_I, [_P, _P, C.c_longlong, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
     "mad_dsc_norms": (_I, [_P, _I, _P, _P]),
     "mad_dsc_to_half": (_I, [_P, _I, _I, _P, _P]),
     "mad_match_segments": (_I, [_I, _I, _I]),

@@ -96,15 +96,21 @@ extern "C" int mad_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 
 static int check_sets(const MadDscSet* hi, const MadDscSet* lo, int impl) {
     MAD_CHECK_ARG(hi && lo && hi->rows >= 0 && lo->rows >= 0);
-    MAD_CHECK_ARG(impl == 0 || impl == 1);
+    MAD_CHECK_ARG(impl == 0 || impl == 1 || impl == 2);
     if (hi->rows == 0 || lo->rows == 0) return MAD_OK;
     MAD_CHECK_ARG(hi->norm2 && lo->norm2);
     if (impl == 1) {
         MAD_CHECK_ARG(hi->dsc && lo->dsc);
     } else {
-        MAD_CHECK_ARG(hi->half && lo->half);
+        if (impl == 2) MAD_CHECK_ARG(hi->half && lo->half);
+        if (impl == 0) MAD_CHECK_ARG(hi->u8 && lo->u8 && lo->rnorm);
         MAD_CHECK_ARG(hi->rows_padded >= hi->rows && hi->rows_padded % 128 == 0);
         MAD_CHECK_ARG(lo->rows_padded >= lo->rows && lo->rows_padded % 128 == 0);
+        if (impl == 0 && (hi->max_entry > 255 || lo->max_entry > 255)) {
+            mad_set_error("mad_match: descriptor entries up to %d do not fit the uint8 kernel (use impl = 2)",
+                          hi->max_entry > lo->max_entry ? hi->max_entry : lo->max_entry);
+            return MAD_ERR_ARG;
+        }
     }
     return MAD_OK;
 }
@@ -119,14 +125,14 @@ static int run_match(const MadDscSet* hi, const MadDscSet* lo, double cc, int mo
                         mode, S, seg_count, seg_offset, pair_hi, pair_lo, pair_score, k, base, topk_idx, topk_score, st);
 }
 
-// Segment count: the tcgen05 kernel's choice for both implementations (same output layout).
+// Segment count: impl 0 = the uint8 kernel's (128-column tiles); 1 and 2 share the fp16 kernel's
+// choice (256-column tiles, same output layout).
 extern "C" int mad_match_segments(int M, int N, int impl) {
-    (void)impl;
-    return mad_match_tc_segments(M, N);
+    return impl == 0 ? mad_match_u8_segments(M, N) : mad_match_tc_segments(M, N);
 }
 
 static int check_segments(const MadDscSet* hi, const MadDscSet* lo, int n_seg) {
-    const int n_tiles = (int)mad_ceil_div(lo->rows, MAD_MATCH_SEG_TILE);
+    const int n_tiles = (int)mad_ceil_div(lo->rows, 128);
     MAD_CHECK_ARG(n_seg >= 1 && n_seg <= (n_tiles > 0 ? n_tiles : 1));
     (void)hi;
     return MAD_OK;
@@ -134,6 +140,7 @@ static int check_segments(const MadDscSet* hi, const MadDscSet* lo, int n_seg) {
 
 extern "C" int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, int32_t* seg_count,
                                int impl, void* stream) {
+    if (impl == 0) impl = 2;
     int rc = check_sets(hi, lo, impl);
     if (rc != MAD_OK) return rc;
     if (hi->rows == 0) return MAD_OK;
@@ -150,6 +157,7 @@ extern "C" int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double 
 
 extern "C" int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, const int64_t* seg_offset,
                               int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int impl, void* stream) {
+    if (impl == 0) impl = 2;
     int rc = check_sets(hi, lo, impl);
     if (rc != MAD_OK) return rc;
     if (hi->rows == 0 || lo->rows == 0) return MAD_OK;
@@ -181,14 +189,18 @@ extern "C" int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, i
         return mad_topk_merge_launch(topk_idx, topk_score, 0, M, k, topk_idx, topk_score, st);
     }
     const int S = mad_match_segments(M, lo->rows, impl);
-    if (S == 1)
-        return run_match(hi, lo, 0.0, 2, 1, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, topk_idx, topk_score,
-                         impl, st);
+    auto run_topk = [&](int segs, int32_t* oi, double* os) {
+        if (impl == 0)
+            return mad_match_u8_topk(hi->u8, hi->rows, hi->rows_padded, lo->u8, lo->rows, lo->rows_padded, hi->norm2,
+                                     lo->norm2, lo->rnorm, segs, k, lo_index_base, oi, os, st);
+        return run_match(hi, lo, 0.0, 2, segs, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, oi, os, impl, st);
+    };
+    if (S == 1) return run_topk(1, topk_idx, topk_score);
     MAD_CHECK_ARG(workspace && workspace_bytes >= mad_match_topk_workspace_bytes(M, lo->rows, k, impl));
     int32_t* pidx = reinterpret_cast<int32_t*>(workspace);
     double* pscore = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) +
                                                mad_align_up((size_t)S * M * k * sizeof(int32_t), 256));
-    rc = run_match(hi, lo, 0.0, 2, S, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, pidx, pscore, impl, st);
+    rc = run_topk(S, pidx, pscore);
     if (rc != MAD_OK) return rc;
     return mad_topk_merge_launch(pidx, pscore, S, M, k, topk_idx, topk_score, st);
 }

@@ -43,3 +43,12 @@ int mad_match_tc(const void* hi_half, int M, int M_pad, const void* lo_half, int
                  int lo_index_base, int32_t* topk_idx, double* topk_score, cudaStream_t st);
 int mad_topk_merge_launch(const int32_t* idx_in, const double* score_in, int G, int M, int k, int32_t* idx_out,
                           double* score_out, cudaStream_t st);
+
+// uint8 tcgen05 kernel (match_u8.cu): 128-column tiles, hi tile resident in shared memory.
+int mad_match_u8_segments(int M, int N);
+int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, int N, int N_pad, const int32_t* hi_n2,
+                       const int32_t* lo_n2, const float* lo_rnorm, double cc, unsigned long long* cand_key,
+                       int32_t* cand_dot, unsigned long long cap, unsigned long long* count, cudaStream_t st);
+int mad_match_u8_topk(const void* hi_u8, int M, int M_pad, const void* lo_u8, int N, int N_pad, const int32_t* hi_n2,
+                      const int32_t* lo_n2, const float* lo_rnorm, int S, int k, int lo_index_base, int32_t* topk_idx,
+                      double* topk_score, cudaStream_t st);

@@ -1,0 +1,454 @@
+// a15: descriptor matching on the 5th-generation tensor cores, 8-bit integer path (sm_100a).
+//
+// Replaces  preds = np.dot(hi_unit, lo_unit.T); np.where(preds > cc)  (mad/MaD.py:416-424).
+// Descriptor entries are vote counts of one 4x4x4-sample sub-block, i.e. integers <= 255 for every
+// patch size the reference uses (<= 24); as uint8 operands of tcgen05.mma.kind::i8 with int32
+// accumulators the raw dot product is EXACT, at twice the fp16 rate and half the operand bytes.
+// The cosine dot / sqrt(n_i n_j) is evaluated in float64 from exact integers for the pairs an
+// fp32 pre-filter cannot rule out.  The M x N score matrix is never written.
+//
+// Why this shape.  With operands streamed from L2 the fp16 kernel (match_tc.cu) needs 48 KB per
+// 4.2 MFLOP, more than the ~43 B/clk/SM the L2 can deliver: it is L2-bound at ~15 % of the tensor
+// peak.  Here the 128-row hi tile (128 x 1024 B = 128 KB) stays RESIDENT in shared memory for the
+// CTA's whole sweep over the lo axis and only lo tiles are streamed: 16 KB per 4.2 MOP.
+//
+//   warp 0      TMA producer : hi tile once (8 boxes of 128 rows x 128 B, 128B swizzle), then the
+//                              lo k-blocks into a 5-stage ring (mbarrier complete_tx)
+//   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128 N=128 K=32, int32
+//                              accumulators in TMEM (4 x 128 columns, 4-deep)
+//   warp 2      TMEM allocator
+//   warps 4..7  epilogue     : tcgen05.ld (32 lanes x 32 columns), thread = one hi row
+//        PAIRS mode: hits (row, col, dot) are staged per warp in shared memory and appended to a
+//                    global candidate list with one atomicAdd per flush; a radix sort by
+//                    (row, col) afterwards restores np.where's row-major order (match_finish).
+//        TOPK mode : per-row running top-k in the thread, one partial list per lo segment.
+#include <cuda.h>
+
+#include "common.cuh"
+#include "match_common.cuh"
+
+namespace {
+
+constexpr int BM = 128;            // hi rows per CTA (UMMA M)
+constexpr int BN = 128;            // lo rows per tile (UMMA N)
+constexpr int BKB = 128;           // bytes (= uint8 elements) per k-block = one 128-byte swizzle row
+constexpr int UKB = 32;            // UMMA K for 8-bit inputs
+constexpr int KBLOCKS = MAD_DSC_LEN / BKB;          // 8
+constexpr int STAGES = 5;
+constexpr int ACCS = 4;            // TMEM accumulator ring (4 x 128 columns)
+constexpr uint32_t KB_BYTES = BM * BKB;             // 16 KB: one k-block of 128 rows
+constexpr uint32_t A_BYTES = KBLOCKS * KB_BYTES;    // 128 KB resident hi tile
+constexpr int THREADS = 256;
+constexpr uint32_t TMEM_COLS = 512;
+constexpr int STG = 320;           // staged hits per epilogue warp
+constexpr size_t STG_BYTES = (size_t)4 * STG * (sizeof(unsigned long long) + sizeof(int));
+// dynamic smem: [1024 slack][A 128K][B ring 80K][staging 15K][barriers, tmem slot, counters 256]
+constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + 256;
+static_assert(SMEM_BYTES <= 232448, "shared memory budget of one sm_100 CTA");
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void umma_i8(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+          "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+          "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile in shared memory, rows of 128 bytes, 128B swizzle (what TMA wrote):
+// start address >> 4, LBO = 1 (unused for swizzled K-major), SBO = 8 rows x 128 B, version 1
+// (Blackwell), layout type 2 = SWIZZLE_128B.
+__device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024u >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+// kind::i8 instruction descriptor: D = s32 (bits 4-5 = 2), A = B = unsigned 8-bit (format 0), both
+// K-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28.
+constexpr uint32_t kIdesc = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+struct U8Args {
+    int M, N, S;                  // rows of hi / lo, number of lo segments
+    int tiles_per_seg;            // 128-column tiles per segment
+    const int32_t* hi_n2;
+    const int32_t* lo_n2;
+    const float* lo_rnorm;        // 1/sqrt(n2) as float, 0 for zero descriptors; padded to N_pad
+    double cc;
+    // PAIRS
+    unsigned long long* cand_key; // (row << 32) | col
+    int32_t* cand_dot;
+    unsigned long long cap;
+    unsigned long long* count;    // device counter (hits found, may exceed cap)
+    // TOPK
+    int k, lo_index_base;
+    int32_t* topk_idx;            // [S][M][k]
+    double* topk_score;
+};
+
+enum { MODE_PAIRS = 0, MODE_TOPK = 1 };
+
+template <int MODE>
+__global__ void __launch_bounds__(THREADS, 1)
+match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, U8Args a) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
+    uint8_t* gen = smem_raw + (base - raw);
+    const uint32_t b_ring = base + A_BYTES;
+    constexpr uint32_t STG_OFF = A_BYTES + STAGES * KB_BYTES;
+    unsigned long long* stg_key = reinterpret_cast<unsigned long long*>(gen + STG_OFF);        // [4][STG]
+    int* stg_dot = reinterpret_cast<int*>(gen + STG_OFF + 4 * STG * sizeof(unsigned long long));   // [4][STG]
+    constexpr uint32_t BAR_OFF = STG_OFF + (uint32_t)STG_BYTES;
+    const uint32_t bars = base + BAR_OFF;
+    auto full_bar = [&](int s) { return bars + 8u * s; };
+    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int q) { return bars + 8u * (2 * STAGES + q); };
+    auto tempty_bar = [&](int q) { return bars + 8u * (2 * STAGES + ACCS + q); };
+    const uint32_t a_bar = bars + 8u * (2 * STAGES + 2 * ACCS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + BAR_OFF + 8 * (2 * STAGES + 2 * ACCS + 1));
+    int* s_cnt = reinterpret_cast<int*>(gen + BAR_OFF + 8 * (2 * STAGES + 2 * ACCS + 2));       // [4]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m0 = blockIdx.x * BM;
+    const int seg = blockIdx.y;
+    const int n_tiles_total = (a.N + BN - 1) / BN;
+    const int t_begin = seg * a.tiles_per_seg;
+    const int t_end = min(n_tiles_total, t_begin + a.tiles_per_seg);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int q = 0; q < ACCS; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 4); }
+        mbar_init(a_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    if (warp == 2) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===================== TMA producer (one elected lane) =====================
+        if (lane == 0) {
+            mbar_expect_tx(a_bar, A_BYTES);
+            for (int kb = 0; kb < KBLOCKS; ++kb) tma_load_2d(base + kb * KB_BYTES, &map_hi, a_bar, kb * BKB, m0);
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = t_begin; t < t_end; ++t) {
+                for (int kb = 0; kb < KBLOCKS; ++kb) {
+                    mbar_wait(empty_bar(stage), phase ^ 1u);
+                    mbar_expect_tx(full_bar(stage), KB_BYTES);
+                    tma_load_2d(b_ring + stage * KB_BYTES, &map_lo, full_bar(stage), kb * BKB, t * BN);
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (one thread) =====================
+        if (lane == 0) {
+            mbar_wait(a_bar, 0);
+            tc_fence_after();
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int t = t_begin; t < t_end; ++t, ++it) {
+                const int acc = it % ACCS;
+                const uint32_t acc_phase = (uint32_t)(it / ACCS) & 1u;
+                mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                for (int kb = 0; kb < KBLOCKS; ++kb) {
+                    mbar_wait(full_bar(stage), phase);
+                    tc_fence_after();
+                    const uint64_t da = umma_smem_desc(base + kb * KB_BYTES);
+                    const uint64_t db = umma_smem_desc(b_ring + stage * KB_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < BKB / UKB; ++kk) {
+                        // advance 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
+                        umma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), kIdesc, (kb | kk) ? 1u : 0u);
+                    }
+                    umma_commit(empty_bar(stage));                   // smem slot free when these MMAs retire
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                }
+                umma_commit(tfull_bar(acc));                         // accumulator complete
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: thread = one hi row =====================
+        const int q = warp & 3;                                      // TMEM lane quadrant of this warp
+        const int row = m0 + q * 32 + lane;
+        const bool row_ok = row < a.M;
+        const int n2a_i = row_ok ? a.hi_n2[row] : 0;
+        const double n2a = (double)n2a_i;
+        const float ra = n2a_i > 0 ? (float)(1.0 / sqrt(n2a)) : 0.f;
+        // fp32 pre-filter: dot * rb > (cc - 4e-6) / ra   (|approx - exact| < 1e-6); never for zero rows
+        const float thr_pairs = (row_ok && n2a_i > 0) ? ((float)a.cc - 4e-6f) / ra : INFINITY;
+        unsigned long long* my_key = stg_key + q * STG;
+        int* my_dot = stg_dot + q * STG;
+        volatile int* my_cnt = s_cnt + q;
+        double bs[MODE == MODE_TOPK ? MAD_TOPK_MAX : 1];
+        int bi[MODE == MODE_TOPK ? MAD_TOPK_MAX : 1];
+        float thr = -1.f;                                            // fp32 bound of the current k-th best
+        if (MODE == MODE_TOPK) {
+#pragma unroll
+            for (int i = 0; i < (MODE == MODE_TOPK ? MAD_TOPK_MAX : 1); ++i) { bs[i] = -INFINITY; bi[i] = -1; }
+        }
+        auto flush = [&]() {
+            // warp-collective: append the staged hits to the global candidate list
+            __syncwarp();
+            const int n = min((int)*my_cnt, STG);
+            if (n > 0) {
+                unsigned long long gb = 0;
+                if (lane == 0) gb = atomicAdd(a.count, (unsigned long long)n);
+                gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
+                for (int i = lane; i < n; i += 32) {
+                    if (gb + i < a.cap) { a.cand_key[gb + i] = my_key[i]; a.cand_dot[gb + i] = my_dot[i]; }
+                }
+            }
+            __syncwarp();
+            if (lane == 0) *my_cnt = 0;
+            __syncwarp();
+        };
+        int it = 0;
+        for (int t = t_begin; t < t_end; ++t, ++it) {
+            const int acc = it % ACCS;
+            const uint32_t acc_phase = (uint32_t)(it / ACCS) & 1u;
+            const int n0 = t * BN;
+            mbar_wait(tfull_bar(acc), acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                uint32_t v[32];
+                tmem_ld32(taddr + (uint32_t)c0, v);
+                float rb[32];
+                const float4* rbp = reinterpret_cast<const float4*>(a.lo_rnorm + n0 + c0);   // padded to a tile multiple
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 r4 = __ldg(rbp + j4);
+                    rb[4 * j4] = r4.x; rb[4 * j4 + 1] = r4.y; rb[4 * j4 + 2] = r4.z; rb[4 * j4 + 3] = r4.w;
+                }
+                tmem_ld_wait();
+#pragma unroll
+                for (int j = 0; j < 32; ++j) {
+                    const int dot = (int)v[j];
+                    const float sc = (float)dot * rb[j];
+                    if (MODE == MODE_TOPK) {
+                        if (row_ok && sc * ra >= thr) {
+                            const int col = n0 + c0 + j;
+                            if (col < a.N) {
+                                const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
+                                mad_topk_insert(bs, bi, a.k, s, a.lo_index_base + col);
+                                const double kth = bs[a.k - 1];
+                                thr = (bi[a.k - 1] < 0) ? -1.f : (float)kth - 4e-6f;
+                            }
+                        }
+                    } else if (sc > thr_pairs) {
+                        const int col = n0 + c0 + j;
+                        if (col < a.N) {
+                            const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
+                            if (s > a.cc) {
+                                const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
+                                const int p = atomicAdd((int*)my_cnt, 1);
+                                if (p < STG) {
+                                    my_key[p] = key;
+                                    my_dot[p] = dot;
+                                } else {                             // staging full (very dense hits): straight to global
+                                    const unsigned long long gp = atomicAdd(a.count, 1ULL);
+                                    if (gp < a.cap) { a.cand_key[gp] = key; a.cand_dot[gp] = dot; }
+                                }
+                            }
+                        }
+                    }
+                }
+                if (MODE == MODE_PAIRS) {
+                    __syncwarp();
+                    if (*my_cnt >= STG / 2) flush();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tempty_bar(acc));             // 4 arrivals free the accumulator
+        }
+        if (MODE == MODE_PAIRS) flush();
+        if (MODE == MODE_TOPK && row_ok) {
+            const long long o = ((long long)seg * a.M + row) * a.k;
+            for (int i = 0; i < a.k; ++i) { a.topk_idx[o + i] = bi[i]; a.topk_score[o + i] = bs[i]; }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// [rows_padded][1024] uint8 row-major; box = 128 bytes (k) x 128 rows, 128-byte swizzle.
+int make_map(CUtensorMap* map, const void* ptr, int rows_padded) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        mad_set_error("mad_match: cuTensorMapEncodeTiled is not available from the CUDA driver");
+        return MAD_ERR_NODEVICE;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)MAD_DSC_LEN, (cuuint64_t)rows_padded};
+    cuuint64_t strides[1] = {(cuuint64_t)MAD_DSC_LEN};
+    cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        mad_set_error("mad_match: cuTensorMapEncodeTiled failed (%d)", (int)r);
+        return MAD_ERR_CUDA;
+    }
+    return MAD_OK;
+}
+
+int check_device() {
+    int dev = 0, major = 0;
+    MAD_CUDA(cudaGetDevice(&dev));
+    MAD_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) {
+        mad_set_error("mad_match: the tcgen05 kernel needs an sm_100 device (found compute capability %d.x)", major);
+        return MAD_ERR_NODEVICE;
+    }
+    return MAD_OK;
+}
+
+}  // namespace
+
+// Number of lo segments: minimises  waves x (tiles per segment + 1)  -- one CTA per SM (224 KB of
+// shared memory), a CTA costs its lo tiles plus one tile-equivalent for loading the hi tile.
+int mad_match_u8_segments(int M, int N) {
+    if (M <= 0 || N <= 0) return 1;
+    const long long m_tiles = mad_ceil_div(M, BM);
+    const long long n_tiles = mad_ceil_div(N, BN);
+    const long long sms = mad_sm_count();
+    long long best_s = 1, best_cost = -1;
+    for (long long s = 1; s <= n_tiles; ++s) {
+        const long long per = mad_ceil_div(n_tiles, s);
+        const long long segs = mad_ceil_div(n_tiles, per);      // no empty segments
+        if (segs != s) continue;
+        const long long cost = mad_ceil_div(m_tiles * s, sms) * (per + 1);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s; }
+    }
+    return (int)best_s;
+}
+
+static int launch_common(const void* hi_u8, int M_pad, const void* lo_u8, int N_pad, CUtensorMap* map_hi, CUtensorMap* map_lo) {
+    int rc = check_device();
+    if (rc != MAD_OK) return rc;
+    rc = make_map(map_hi, hi_u8, M_pad);
+    if (rc != MAD_OK) return rc;
+    return make_map(map_lo, lo_u8, N_pad);
+}
+
+int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, int N, int N_pad, const int32_t* hi_n2,
+                       const int32_t* lo_n2, const float* lo_rnorm, double cc, unsigned long long* cand_key,
+                       int32_t* cand_dot, unsigned long long cap, unsigned long long* count, cudaStream_t st) {
+    CUtensorMap map_hi, map_lo;
+    int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, &map_hi, &map_lo);
+    if (rc != MAD_OK) return rc;
+    U8Args a = {};
+    a.M = M; a.N = N;
+    a.S = mad_match_u8_segments(M, N);
+    a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN), a.S);
+    a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = cc;
+    a.cand_key = cand_key; a.cand_dot = cand_dot; a.cap = cap; a.count = count;
+    MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    dim3 grid((unsigned)mad_ceil_div(M, BM), (unsigned)a.S);
+    MAD_PROF("match_u8_pairs_kernel", st);
+    match_u8_kernel<MODE_PAIRS><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}
+
+int mad_match_u8_topk(const void* hi_u8, int M, int M_pad, const void* lo_u8, int N, int N_pad, const int32_t* hi_n2,
+                      const int32_t* lo_n2, const float* lo_rnorm, int S, int k, int lo_index_base, int32_t* topk_idx,
+                      double* topk_score, cudaStream_t st) {
+    CUtensorMap map_hi, map_lo;
+    int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, &map_hi, &map_lo);
+    if (rc != MAD_OK) return rc;
+    U8Args a = {};
+    a.M = M; a.N = N; a.S = S;
+    a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN), S);
+    a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = 0.0;
+    a.k = k; a.lo_index_base = lo_index_base; a.topk_idx = topk_idx; a.topk_score = topk_score;
+    MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+    dim3 grid((unsigned)mad_ceil_div(M, BM), (unsigned)S);
+    MAD_PROF("match_u8_topk_kernel", st);
+    match_u8_kernel<MODE_TOPK><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}

@@ -370,14 +370,17 @@ template <typename ACC> struct Wt;
 template <> struct Wt<double> { static __device__ __forceinline__ double get(double w) { return w; } };
 template <> struct Wt<float> { static __device__ __forceinline__ float get(double w) { return (float)w; } };
 
+// The sliding windows hold the samples ALREADY CONVERTED to the accumulation type: one
+// F2F.F64.F32 per loaded sample instead of one per tap (the conversion runs at 1/8 of the FP64
+// FMA rate and was the bound of the first version of these kernels).
 template <int R, typename ACC>
-__device__ __forceinline__ void conv_both(const float* win, int t, const ConvW& w, float& o0, float& o2) {
-    const ACC c = (ACC)win[t + R];
+__device__ __forceinline__ void conv_both(const ACC* win, int t, const ConvW& w, float& o0, float& o2) {
+    const ACC c = win[t + R];
     ACC a0 = c * Wt<ACC>::get(w.w0[0]);
     ACC a2 = c * Wt<ACC>::get(w.w2[0]);
 #pragma unroll
     for (int jj = R; jj >= 1; --jj) {
-        const ACC s = (ACC)win[t + R - jj] + (ACC)win[t + R + jj];
+        const ACC s = win[t + R - jj] + win[t + R + jj];
         a0 = fma(s, Wt<ACC>::get(w.w0[jj]), a0);
         a2 = fma(s, Wt<ACC>::get(w.w2[jj]), a2);
     }
@@ -386,38 +389,41 @@ __device__ __forceinline__ void conv_both(const float* win, int t, const ConvW& 
 }
 
 template <int R, typename ACC>
-__device__ __forceinline__ float conv_g(const float* win, int t, const ConvW& w) {
-    ACC a0 = (ACC)win[t + R] * Wt<ACC>::get(w.w0[0]);
+__device__ __forceinline__ float conv_g(const ACC* win, int t, const ConvW& w) {
+    ACC a0 = win[t + R] * Wt<ACC>::get(w.w0[0]);
 #pragma unroll
     for (int jj = R; jj >= 1; --jj) {
-        const ACC s = (ACC)win[t + R - jj] + (ACC)win[t + R + jj];
+        const ACC s = win[t + R - jj] + win[t + R + jj];
         a0 = fma(s, Wt<ACC>::get(w.w0[jj]), a0);
     }
     return (float)a0;
 }
 
 // MODE 0: pass X (in0=f; o0=P0, o1=Q0).  MODE 1: pass Y (in0=P0, in1=Q0; o0=P01, o1=R, o2=S).
+// One thread per line, marching along the (strided) axis; consecutive threads own consecutive z,
+// so every load and store of a warp is one coalesced 128-byte line.
 template <int R, typename ACC, int MODE>
 __global__ void __launch_bounds__(128)
 log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ o0,
                         float* __restrict__ o1, float* __restrict__ o2, int n, long long inner,
                         long long total_lines, int seg_len, ConvW w) {
-    constexpr int T = 16, W = T + 2 * R;
+    constexpr int T = 8, W = T + 2 * R;
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= total_lines) return;
     const long long o = g / inner, j = g % inner;
     const long long base = o * (long long)n * inner + j;
     const int a0 = blockIdx.y * seg_len;
     const int a1 = min(n, a0 + seg_len);
-    float wa[W];
-    float wb[MODE == 1 ? W : 1];
+    ACC wa[W];
+    ACC wb[MODE == 1 ? W : 1];
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i) {
         const long long off = base + (long long)mad_reflect(a0 - R + i, n) * inner;
-        wa[i] = __ldg(in0 + off);
-        if (MODE == 1) wb[i] = __ldg(in1 + off);
+        wa[i] = (ACC)__ldg(in0 + off);
+        if (MODE == 1) wb[i] = (ACC)__ldg(in1 + off);
     }
     for (int a = a0; a < a1; a += T) {
+        float la[T], lb[MODE == 1 ? T : 1];
 #pragma unroll
         for (int i = 0; i < T; ++i) {
             const int pos = a + R + i;
@@ -427,8 +433,13 @@ log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__
                 va = __ldg(in0 + off);
                 if (MODE == 1) vb = __ldg(in1 + off);
             }
-            wa[2 * R + i] = va;
-            if (MODE == 1) wb[2 * R + i] = vb;
+            la[i] = va;
+            if (MODE == 1) lb[i] = vb;
+        }
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            wa[2 * R + i] = (ACC)la[i];
+            if (MODE == 1) wb[2 * R + i] = (ACC)lb[i];
         }
 #pragma unroll
         for (int t = 0; t < T; ++t) {
@@ -449,6 +460,9 @@ log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__
     }
 }
 
+// Pass Z (contiguous axis): rows are staged in shared memory with coalesced loads (reflect halo
+// applied while staging); a thread produces T consecutive outputs of one row from a register
+// window converted once to the accumulation type, one array after the other.
 template <int R, typename ACC>
 __global__ void __launch_bounds__(128)
 log_pass_z_kernel(const float* __restrict__ P01, const float* __restrict__ Rr, const float* __restrict__ S,
@@ -484,29 +498,33 @@ log_pass_z_kernel(const float* __restrict__ P01, const float* __restrict__ Rr, c
     for (int it = tid; it < rows * n_chunks; it += blockDim.x) {
         const int r = it / n_chunks, c = it % n_chunks;
         const int z0 = c * T;
-        float wa[W], wb[W], wc[W];
-        const float4* pa = reinterpret_cast<const float4*>(sin0 + r * rs_in + z0);
-        const float4* pb = reinterpret_cast<const float4*>(sin1 + r * rs_in + z0);
-        const float4* pc = reinterpret_cast<const float4*>(sin2 + r * rs_in + z0);
+        ACC win[W];
+        auto load_window = [&](const float* src) {
+            const float4* p = reinterpret_cast<const float4*>(src + r * rs_in + z0);
 #pragma unroll
-        for (int q = 0; q < W / 4; ++q) {
-            const float4 va = pa[q], vb = pb[q], vc = pc[q];
-            wa[4 * q] = va.x; wa[4 * q + 1] = va.y; wa[4 * q + 2] = va.z; wa[4 * q + 3] = va.w;
-            wb[4 * q] = vb.x; wb[4 * q + 1] = vb.y; wb[4 * q + 2] = vb.z; wb[4 * q + 3] = vb.w;
-            wc[4 * q] = vc.x; wc[4 * q + 1] = vc.y; wc[4 * q + 2] = vc.z; wc[4 * q + 3] = vc.w;
-        }
+            for (int q = 0; q < W / 4; ++q) {
+                const float4 v = p[q];
+                win[4 * q] = (ACC)v.x; win[4 * q + 1] = (ACC)v.y; win[4 * q + 2] = (ACC)v.z; win[4 * q + 3] = (ACC)v.w;
+            }
+        };
+        float gs[T], t3[T], t2[T], t1[T];
+        load_window(sin0);
+#pragma unroll
+        for (int t = 0; t < T; ++t) conv_both<R, ACC>(win, t, w, gs[t], t3[t]);
+        load_window(sin1);
+#pragma unroll
+        for (int t = 0; t < T; ++t) t2[t] = conv_g<R, ACC>(win, t, w);
+        load_window(sin2);
+#pragma unroll
+        for (int t = 0; t < T; ++t) t1[t] = conv_g<R, ACC>(win, t, w);
 #pragma unroll
         for (int t = 0; t < T; ++t) {
-            float gs, t3;
-            conv_both<R, ACC>(wa, t, w, gs, t3);
-            const float t2 = conv_g<R, ACC>(wb, t, w);
-            const float t1 = conv_g<R, ACC>(wc, t, w);
-            const float lap = __fadd_rn(__fadd_rn(t1, t2), t3);
+            const float lap = __fadd_rn(__fadd_rn(t1[t], t2[t]), t3[t]);
             float m = __fmul_rn(-lap, scale);
             if (m < 0.f) m = 0.f;
             if (z0 + t < nz) {
                 sout0[r * rs_out + z0 + t] = m;
-                sout1[r * rs_out + z0 + t] = gs;
+                sout1[r * rs_out + z0 + t] = gs[t];
             }
         }
     }

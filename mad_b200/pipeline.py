@@ -291,9 +291,11 @@ def describe_struct(grid, patch_size=16, map_padding=9, sig_init=2, sig_presmoot
 # a15 matching
 # ---------------------------------------------------------------------------------------------
 class DescriptorSet(object):
-    """int16 descriptors prepared for matching: exact norms (+ fp16 operand for tcgen05)."""
+    """int16 descriptors prepared for matching: exact norms, the uint8 tensor-core operand
+    (tcgen05 kind::i8, exact while every entry <= 255) and, on demand, an fp16 copy for the general
+    tensor-core kernel (impl 2)."""
 
-    def __init__(self, dsc, need_half=True):
+    def __init__(self, dsc, need_half=False):
         _require_cuda()
         if isinstance(dsc, np.ndarray):
             dsc = torch.from_numpy(np.ascontiguousarray(dsc, dtype=np.int16)).cuda()
@@ -302,35 +304,78 @@ class DescriptorSet(object):
         dev = self.dsc.device
         st = _stream()
         self.rows = self.dsc.shape[0]
-        self.rows_padded = (self.rows + 127) // 128 * 128
+        self.rows_padded = max((self.rows + 127) // 128 * 128, 128)
         self.norm2 = torch.empty(max(self.rows, 1), dtype=torch.int32, device=dev)
-        call("mad_dsc_norms", _ptr(self.dsc), self.rows, _ptr(self.norm2), st)
+        self.rnorm = torch.empty(self.rows_padded, dtype=torch.float32, device=dev)
+        self.u8 = torch.empty((self.rows_padded, DSC_LEN), dtype=torch.uint8, device=dev)
+        mx = torch.zeros(1, dtype=torch.int32, device=dev)
+        call("mad_dsc_prepare", _ptr(self.dsc), self.rows, self.rows_padded, _ptr(self.norm2), _ptr(self.rnorm),
+             _ptr(self.u8), _ptr(mx), st)
+        self._max_dev = mx
+        self._max_entry = None
         self.half = None
-        if need_half:
-            self.half = torch.empty((max(self.rows_padded, 128), DSC_LEN), dtype=torch.float16, device=dev)
-            call("mad_dsc_to_half", _ptr(self.dsc), self.rows, self.rows_padded, _ptr(self.half), st)
         s = _lib.MadDscSet()
         s.dsc = self.dsc.data_ptr()
-        s.half = self.half.data_ptr() if self.half is not None else 0
+        s.half = 0
         s.norm2 = self.norm2.data_ptr()
+        s.u8 = self.u8.data_ptr()
+        s.rnorm = self.rnorm.data_ptr()
         s.rows, s.rows_padded = self.rows, self.rows_padded
+        s.max_entry = -1
         self.c = s
+        if need_half:
+            self.ensure_half()
+
+    @property
+    def max_entry(self):
+        """Largest descriptor entry (one device->host read, cached)."""
+        if self._max_entry is None:
+            self._max_entry = int(self._max_dev.item())
+            self.c.max_entry = self._max_entry
+        return self._max_entry
+
+    def ensure_half(self):
+        if self.half is None:
+            self.half = torch.empty((self.rows_padded, DSC_LEN), dtype=torch.float16, device=self.dsc.device)
+            call("mad_dsc_to_half", _ptr(self.dsc), self.rows, self.rows_padded, _ptr(self.half), _stream())
+            self.c.half = self.half.data_ptr()
+        return self
 
 
-def _as_set(x, impl):
-    return x if isinstance(x, DescriptorSet) else DescriptorSet(x, need_half=(impl == 0))
+def _as_set(x):
+    return x if isinstance(x, DescriptorSet) else DescriptorSet(x)
 
 
-def match_threshold(hi, lo, cc=0.6, impl=0):
+def _pick_impl(hi, lo, impl):
+    """impl None = product choice: the uint8 tcgen05 kernel, or the fp16 one if an entry exceeds 255."""
+    if impl is None:
+        impl = 0 if max(hi.max_entry, lo.max_entry) <= 255 else 2
+    if impl == 0:
+        hi.max_entry, lo.max_entry          # noqa: B018  (fills the C structs)
+    if impl == 2:
+        hi.ensure_half()
+        lo.ensure_half()
+    return impl
+
+
+_PAIR_CAP = {}
+
+
+def match_threshold(hi, lo, cc=0.6, impl=None):
     """Pairs (i, j) with cosine(hi_i, lo_j) > cc in row-major order (mad/MaD.py:420-424).
-    Returns (hi index int32 [P], lo index int32 [P], score float64 [P]) as device tensors."""
-    hi, lo = _as_set(hi, impl), _as_set(lo, impl)
+    Returns (hi index int32 [P], lo index int32 [P], score float64 [P]) as device tensors.
+    impl: None/0 = one-pass uint8 tcgen05 kernel + sort (product), 1 = SIMT check kernel,
+    2 = fp16 tcgen05 kernel (both two-pass count/fill)."""
+    hi, lo = _as_set(hi), _as_set(lo)
     dev = hi.dsc.device
     st = _stream()
     m = hi.rows
     if m == 0 or lo.rows == 0:
         e = torch.empty(0, dtype=torch.int32, device=dev)
         return e, e.clone(), torch.empty(0, dtype=torch.float64, device=dev)
+    impl = _pick_impl(hi, lo, impl)
+    if impl == 0:
+        return _match_threshold_onepass(hi, lo, cc, dev, st)
     n_seg = int(_lib.lib.mad_match_segments(m, lo.rows, impl))
     seg_count = torch.empty(m * n_seg, dtype=torch.int32, device=dev)
     call("mad_match_count", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), n_seg, _ptr(seg_count), impl, st)
@@ -348,11 +393,37 @@ def match_threshold(hi, lo, cc=0.6, impl=0):
     return pair_hi[:p], pair_lo[:p], score[:p]
 
 
-def match_topk(hi, lo, k=8, lo_index_base=0, impl=0):
+def _match_threshold_onepass(hi, lo, cc, dev, st):
+    key = (hi.rows, lo.rows)
+    cap = _PAIR_CAP.get(key, max(1 << 20, 16 * (hi.rows + lo.rows)))
+    while True:
+        cand_key = torch.empty(cap, dtype=torch.int64, device=dev)
+        cand_dot = torch.empty(cap, dtype=torch.int32, device=dev)
+        count = torch.empty(1, dtype=torch.int64, device=dev)
+        call("mad_match_pairs", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), _ptr(cand_key), _ptr(cand_dot),
+             C.c_uint64(cap), _ptr(count), st)
+        p = int(count.item())
+        if p <= cap:
+            break
+        cap = p + p // 8 + 1024            # the candidate list overflowed: repeat with room
+    _PAIR_CAP[key] = max(cap, p + p // 4)
+    pair_hi = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
+    pair_lo = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
+    score = torch.empty(max(p, 1), dtype=torch.float64, device=dev)
+    if p:
+        ws_bytes = _lib.lib.mad_match_pairs_finish_workspace_bytes(p)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        call("mad_match_pairs_finish", _ptr(cand_key), _ptr(cand_dot), p, hi.rows, _ptr(hi.norm2), _ptr(lo.norm2),
+             _ptr(pair_hi), _ptr(pair_lo), _ptr(score), _ptr(ws), ws_bytes, st)
+    return pair_hi[:p], pair_lo[:p], score[:p]
+
+
+def match_topk(hi, lo, k=8, lo_index_base=0, impl=None):
     """Per hi row the k best lo rows by (score desc, index asc).  Device tensors (idx, score)."""
-    hi, lo = _as_set(hi, impl), _as_set(lo, impl)
+    hi, lo = _as_set(hi), _as_set(lo)
     dev = hi.dsc.device
     st = _stream()
+    impl = _pick_impl(hi, lo, impl)
     idx = torch.empty((hi.rows, k), dtype=torch.int32, device=dev)
     score = torch.empty((hi.rows, k), dtype=torch.float64, device=dev)
     ws_bytes = _lib.lib.mad_match_topk_workspace_bytes(hi.rows, lo.rows, int(k), impl)
