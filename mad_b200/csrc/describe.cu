@@ -20,12 +20,33 @@ __device__ __forceinline__ int nearest_idx(double p, int n) {
     return (p - (double)i <= 0.5) ? i : i + 1;     // scipy _rgi: where(norm_dist <= .5, i, i + 1)
 }
 
-__global__ void __launch_bounds__(256)
+// Exact (reference-arithmetic) classification of one direction: float64 rotation, atan2, acos and
+// the strict-inequality zone test.  Kept out of line: it runs for ~0.1 % of the samples and must
+// not set the register budget of the main loop.
+__device__ __noinline__ int zone_exact_dsc(ZoneTab T, const double* __restrict__ Rm, float gx, float gy, float gz) {
+    const double vx0 = gx, vy0 = gy, vz0 = gz;
+    const double vx = (vx0 * Rm[0] + vy0 * Rm[1]) + vz0 * Rm[2];
+    const double vy = (vx0 * Rm[3] + vy0 * Rm[4]) + vz0 * Rm[5];
+    const double vz = (vx0 * Rm[6] + vy0 * Rm[7]) + vz0 * Rm[8];
+    double th = atan2(vy, vx);
+    if (th < 0.0) th += MAD_TWO_PI;
+    const double sth = th + MAD_TWO_PI;
+    const double ph = acos(fmin(1.0, fmax(-1.0, vz)));
+    int z[2];
+    const int nzn = zones_of(T, th, sth, ph, z);
+    if (nzn == 1) return z[0];
+    if (nzn >= 2) return max(z[0], z[1]);           // ascending assignment: the higher index wins
+    return 0;                                       // unassigned directions stay in zone 0 (:173)
+}
+
+__global__ void __launch_bounds__(256, 3)
 describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1, OctDims dims,
                 const MadKeypoint* __restrict__ kp, const MadOriented* __restrict__ oriented, int r,
                 ZoneTab T, const double* __restrict__ rf_table, const double* __restrict__ rf_inv_table,
                 int rf_zones, int16_t* __restrict__ dsc) {
     __shared__ int cnt[MAD_DSC_LEN];
+    __shared__ ZoneFast F;
+    __shared__ int s_bad;
     const int tid = threadIdx.x;
     const MadOriented of = oriented[blockIdx.x];
     const MadKeypoint K = kp[of.kp];
@@ -33,9 +54,10 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
     const float4* __restrict__ grad = o ? grad1 : grad0;
     const int nx = dims.n[o][0], ny = dims.n[o][1], nz = dims.n[o][2];
     const long long tab = ((long long)of.main_bin * rf_zones + of.sec_bin) * 9;
-    double Rm[9], Ri[9];
+    double Ri[9];
+    float Rmf[9];
 #pragma unroll
-    for (int q = 0; q < 9; ++q) { Rm[q] = rf_table[tab + q]; Ri[q] = rf_inv_table[tab + q]; }
+    for (int q = 0; q < 9; ++q) { Ri[q] = rf_inv_table[tab + q]; Rmf[q] = (float)rf_table[tab + q]; }
     const int side = 2 * r;
     const int total = side * side * side;
     const int c1 = r / 2, c2 = r, c3 = (3 * r) / 2;
@@ -44,20 +66,27 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
     const double du = o ? 1.0 : 2.0;
 
     for (int q = tid; q < MAD_DSC_LEN; q += blockDim.x) cnt[q] = 0;
+    zone_fast_init(&F, T);
+    if (tid == 0) s_bad = 0;
+    __syncthreads();
 
-    // pass 1: whole-patch bounds vote (RegularGridInterpolator bounds_error)
-    int bad = 0;
-    for (int sidx = tid; sidx < total; sidx += blockDim.x) {
-        const int k = sidx % side, j = (sidx / side) % side, i = sidx / (side * side);
-        const double lx = u0 + du * i, ly = u0 + du * j, lz = u0 + du * k;
+    // Whole-patch bounds vote (RegularGridInterpolator bounds_error, mad/Descriptor.py:140-149).
+    // Each coordinate ((lx*a + ly*b) + lz*c) + centre is a monotone function of lx, ly and lz in
+    // IEEE arithmetic (rounding is monotone), so its extremes over the lattice are taken at the 8
+    // corners: testing them is exactly equivalent to testing all (2r)^3 samples.
+    if (tid < 8) {
+        const double lx = u0 + du * ((tid & 1) ? side - 1 : 0);
+        const double ly = u0 + du * ((tid & 2) ? side - 1 : 0);
+        const double lz = u0 + du * ((tid & 4) ? side - 1 : 0);
         const double px = ((lx * Ri[0] + ly * Ri[1]) + lz * Ri[2]) + cx;
         const double py = ((lx * Ri[3] + ly * Ri[4]) + lz * Ri[5]) + cy;
         const double pz = ((lx * Ri[6] + ly * Ri[7]) + lz * Ri[8]) + cz;
-        if (px < 0.0 || px > (double)(nx - 1) || py < 0.0 || py > (double)(ny - 1) || pz < 0.0 || pz > (double)(nz - 1)) bad = 1;
+        if (px < 0.0 || px > (double)(nx - 1) || py < 0.0 || py > (double)(ny - 1) || pz < 0.0 || pz > (double)(nz - 1))
+            atomicOr(&s_bad, 1);
     }
-    const int any_bad = __syncthreads_or(bad);
+    __syncthreads();
     int16_t* out = dsc + (long long)blockIdx.x * MAD_DSC_LEN;
-    if (any_bad) {
+    if (s_bad) {
         for (int q = tid; q < MAD_DSC_LEN; q += blockDim.x) out[q] = 0;
         return;
     }
@@ -77,19 +106,11 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
             g.y = __fdiv_rn(g.y, m);
             g.z = __fdiv_rn(g.z, m);
         }
-        const double vx0 = g.x, vy0 = g.y, vz0 = g.z;
-        const double vx = (vx0 * Rm[0] + vy0 * Rm[1]) + vz0 * Rm[2];
-        const double vy = (vx0 * Rm[3] + vy0 * Rm[4]) + vz0 * Rm[5];
-        const double vz = (vx0 * Rm[6] + vy0 * Rm[7]) + vz0 * Rm[8];
-        double th = atan2(vy, vx);
-        if (th < 0.0) th += MAD_TWO_PI;
-        const double sth = th + MAD_TWO_PI;
-        const double ph = acos(fmin(1.0, fmax(-1.0, vz)));
-        int z[2];
-        const int nzn = zones_of(T, th, sth, ph, z);
-        int zone = 0;                               // unassigned directions stay in zone 0 (:173)
-        if (nzn == 1) zone = z[0];
-        else if (nzn >= 2) zone = max(z[0], z[1]);  // ascending assignment: the higher index wins
+        // float32 classification; directions within 2e-5 rad of a zone edge take the exact path
+        int zone = zone_fast(F, (g.x * Rmf[0] + g.y * Rmf[1]) + g.z * Rmf[2],
+                             (g.x * Rmf[3] + g.y * Rmf[4]) + g.z * Rmf[5],
+                             (g.x * Rmf[6] + g.y * Rmf[7]) + g.z * Rmf[8]);
+        if (zone < 0) zone = zone_exact_dsc(T, rf_table + tab, g.x, g.y, g.z);
         const int bx = (i >= c1) + (i >= c2) + (i >= c3);
         const int by = (j >= c1) + (j >= c2) + (j >= c3);
         const int bz = (k >= c1) + (k >= c2) + (k >= c3);

@@ -48,3 +48,65 @@ __device__ __forceinline__ int zones_of(const ZoneTab& T, double th, double sth,
     if (zone_has(T, c2, th, sth)) { if (n < 2) z[n] = c2; ++n; }
     return n < 2 ? n : 2;
 }
+
+// ------------------------------------------------------------------------------------------
+// Fast classification.  The exact rule above needs atan2/acos in float64 (hundreds of FP64
+// instructions per sample).  A direction that is farther than MAD_ZONE_EPS (2e-5 rad) from every
+// zone edge gets the same zone from float32 arithmetic (float32 rotation + atan2f: error below
+// 2e-6 rad away from the poles; the polar caps need no theta at all).  zone_fast returns that
+// zone, or -1 for the ~0.1 % of directions near an edge, which then take the exact path.
+// ------------------------------------------------------------------------------------------
+#define MAD_ZONE_EPS 2e-5
+#define MAD_ZONE_MAX 128
+#define MAD_BELT_MAX 32
+
+struct ZoneFast {                    // per-CTA copy in shared memory (zone_fast_init)
+    float tmin[MAD_ZONE_MAX];        // theta bounds shrunk by eps
+    float tmax[MAD_ZONE_MAX];
+    float vz_hi[MAD_BELT_MAX];       // belt b certain iff vz_lo[b] < vz < vz_hi[b]
+    float vz_lo[MAD_BELT_MAX];
+    float t0[MAD_BELT_MAX];          // theta_min of the belt's first zone
+    float k_scale[MAD_BELT_MAX];     // zones / 2 pi
+    int first[MAD_BELT_MAX + 1];
+    int n_belts;
+};
+
+__device__ __forceinline__ void zone_fast_init(ZoneFast* F, const ZoneTab& T) {
+    for (int a = threadIdx.x; a < T.n_zones; a += blockDim.x) {
+        F->tmin[a] = (float)(T.bounds[4 * a + 0] + MAD_ZONE_EPS);
+        F->tmax[a] = (float)(T.bounds[4 * a + 2] - MAD_ZONE_EPS);
+    }
+    for (int b = threadIdx.x; b <= T.n_belts; b += blockDim.x) {
+        F->first[b] = T.belt_first[b];
+        if (b < T.n_belts) {
+            // cos is decreasing on [0, pi]; 1e-6 covers the float32 error of the rotated z component
+            F->vz_hi[b] = (float)(cos(T.belt_phi[b] + MAD_ZONE_EPS) - 1e-6);
+            F->vz_lo[b] = (float)(cos(T.belt_phi[b + 1] - MAD_ZONE_EPS) + 1e-6);
+            const int f = T.belt_first[b];
+            F->t0[b] = (float)T.bounds[4 * f + 0];
+            F->k_scale[b] = (float)((double)(T.belt_first[b + 1] - f) / MAD_TWO_PI);
+        }
+    }
+    if (threadIdx.x == 0) F->n_belts = T.n_belts;
+}
+
+// (vx, vy, vz): unit direction in float32.  Returns the zone, or -1 if the exact test must decide.
+__device__ __forceinline__ int zone_fast(const ZoneFast& F, float vx, float vy, float vz) {
+    int b = -1;
+    for (int k = 0; k < F.n_belts; ++k)
+        if (vz < F.vz_hi[k] && vz > F.vz_lo[k]) { b = k; break; }
+    if (b < 0) return -1;
+    const int first = F.first[b];
+    const int nb = F.first[b + 1] - first;
+    if (nb == 1) return first;                       // polar cap: every theta passes (0 via theta + 2 pi)
+    float th = atan2f(vy, vx);
+    if (th < 0.f) th += 6.2831855f;
+    float u = th - F.t0[b];
+    if (u < 0.f) u += 6.2831855f;
+    int k = (int)(u * F.k_scale[b]);
+    k = min(k, nb - 1);
+    const int z = first + k;
+    const float sth = th + 6.2831855f;
+    if ((th > F.tmin[z] && th < F.tmax[z]) || (sth > F.tmin[z] && sth < F.tmax[z])) return z;
+    return -1;
+}

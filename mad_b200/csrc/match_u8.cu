@@ -40,10 +40,11 @@ constexpr uint32_t KB_BYTES = BM * BKB;             // 16 KB: one k-block of 128
 constexpr uint32_t A_BYTES = KBLOCKS * KB_BYTES;    // 128 KB resident hi tile
 constexpr int THREADS = 256;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int STG = 320;           // staged hits per epilogue warp
+constexpr int STG = 192;           // staged candidates per epilogue warp
 constexpr size_t STG_BYTES = (size_t)4 * STG * (sizeof(unsigned long long) + sizeof(int));
-// dynamic smem: [1024 slack][A 128K][B ring 80K][staging 15K][barriers, tmem slot, counters 256]
-constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + 256;
+constexpr size_t RB_BYTES = (size_t)4 * 2 * BN * sizeof(float);   // per-warp, double-buffered 1/|lo| of a tile
+// dynamic smem: [1024 slack][A 128K][B ring 80K][staging 9K][rnorm 4K][barriers, tmem slot, counters 256]
+constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + RB_BYTES + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one sm_100 CTA");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -97,6 +98,11 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ uint32_t tmem_ld1(uint32_t taddr) {
+    uint32_t x;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(x) : "r"(taddr) : "memory");
+    return x;
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -148,7 +154,8 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     constexpr uint32_t STG_OFF = A_BYTES + STAGES * KB_BYTES;
     unsigned long long* stg_key = reinterpret_cast<unsigned long long*>(gen + STG_OFF);        // [4][STG]
     int* stg_dot = reinterpret_cast<int*>(gen + STG_OFF + 4 * STG * sizeof(unsigned long long));   // [4][STG]
-    constexpr uint32_t BAR_OFF = STG_OFF + (uint32_t)STG_BYTES;
+    float* s_rb = reinterpret_cast<float*>(gen + STG_OFF + (uint32_t)STG_BYTES);                  // [4][2][BN]
+    constexpr uint32_t BAR_OFF = STG_OFF + (uint32_t)(STG_BYTES + RB_BYTES);
     const uint32_t bars = base + BAR_OFF;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
@@ -247,27 +254,52 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
 #pragma unroll
             for (int i = 0; i < (MODE == MODE_TOPK ? MAD_TOPK_MAX : 1); ++i) { bs[i] = -INFINITY; bi[i] = -1; }
         }
+        // Candidates that pass the fp32 pre-filter are only STAGED here (two shared-memory stores);
+        // the float64 test runs at flush time with the lanes working on 32 candidates in parallel,
+        // so its latency (L2 load of the lo norm, DSQRT, DDIV) is not serialised per hit.
+        auto exact_and_emit = [&](unsigned long long key, int dot, bool have) {
+            bool ok = false;
+            if (have) {
+                const int r = (int)(key >> 32), c = (int)(key & 0xFFFFFFFFull);
+                if (r < a.M && c < a.N) {
+                    const double s = mad_score(dot, (double)__ldg(a.hi_n2 + r), (double)__ldg(a.lo_n2 + c));
+                    ok = s > a.cc;
+                }
+            }
+            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+            if (m) {
+                unsigned long long gb = 0;
+                if (lane == 0) gb = atomicAdd(a.count, (unsigned long long)__popc(m));
+                gb = __shfl_sync(0xFFFFFFFFu, gb, 0) + __popc(m & ((1u << lane) - 1u));
+                if (ok && gb < a.cap) { a.cand_key[gb] = key; a.cand_dot[gb] = dot; }
+            }
+        };
         auto flush = [&]() {
-            // warp-collective: append the staged hits to the global candidate list
             __syncwarp();
             const int n = min((int)*my_cnt, STG);
-            if (n > 0) {
-                unsigned long long gb = 0;
-                if (lane == 0) gb = atomicAdd(a.count, (unsigned long long)n);
-                gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
-                for (int i = lane; i < n; i += 32) {
-                    if (gb + i < a.cap) { a.cand_key[gb + i] = my_key[i]; a.cand_dot[gb + i] = my_dot[i]; }
-                }
+            for (int i0 = 0; i0 < n; i0 += 32) {
+                const int i = i0 + lane;
+                const bool have = i < n;
+                exact_and_emit(have ? my_key[i] : 0ull, have ? my_dot[i] : 0, have);
             }
             __syncwarp();
             if (lane == 0) *my_cnt = 0;
             __syncwarp();
         };
+        float* my_rb = s_rb + q * 2 * BN;
+        auto stage_rb = [&](int t, int buf) {                        // 128 floats of this tile: lane -> one float4
+            const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.lo_rnorm + (long long)t * BN) + lane);
+            reinterpret_cast<float4*>(my_rb + buf * BN)[lane] = r4;
+        };
         int it = 0;
+        if (t_begin < t_end) stage_rb(t_begin, 0);
         for (int t = t_begin; t < t_end; ++t, ++it) {
             const int acc = it % ACCS;
             const uint32_t acc_phase = (uint32_t)(it / ACCS) & 1u;
             const int n0 = t * BN;
+            if (t + 1 < t_end) stage_rb(t + 1, (it + 1) & 1);        // next tile's norms: latency hidden by this tile
+            __syncwarp();
+            const float* rbt = my_rb + (it & 1) * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -276,41 +308,51 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
                 float rb[32];
-                const float4* rbp = reinterpret_cast<const float4*>(a.lo_rnorm + n0 + c0);   // padded to a tile multiple
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 r4 = __ldg(rbp + j4);
+                    const float4 r4 = reinterpret_cast<const float4*>(rbt + c0)[j4];
                     rb[4 * j4] = r4.x; rb[4 * j4 + 1] = r4.y; rb[4 * j4 + 2] = r4.z; rb[4 * j4 + 3] = r4.w;
                 }
                 tmem_ld_wait();
+                // Branch-free pre-filter over the 32 columns (the epilogue must stay small: an unrolled
+                // branchy body overflowed the instruction cache and made the epilogue the bottleneck);
+                // the rare candidates are then fetched again from TMEM one column at a time.
+                const float lim = (MODE == MODE_TOPK) ? (row_ok && ra > 0.f ? thr / ra : INFINITY) : thr_pairs;
+                unsigned mask = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    const int dot = (int)v[j];
-                    const float sc = (float)dot * rb[j];
+                    const float sc = (float)(int)v[j] * rb[j];
+                    const bool pass = (MODE == MODE_TOPK) ? (sc >= lim) : (sc > lim);
+                    mask |= (pass ? 1u : 0u) << j;
+                }
+                // zero row: every score is 0 and ties go to the lowest index -- only the first k columns matter
+                if (MODE == MODE_TOPK && row_ok && ra == 0.f) mask = (bi[a.k - 1] < 0) ? 0xFFFFFFFFu : 0u;
+                unsigned any = __reduce_or_sync(0xFFFFFFFFu, mask);
+                while (any) {
+                    const int j = __ffs(any) - 1;
+                    any &= any - 1;
+                    const int dot = (int)tmem_ld1(taddr + (uint32_t)(c0 + j));
+                    tmem_ld_wait();
+                    if (!((mask >> j) & 1u)) continue;
+                    const int col = n0 + c0 + j;
                     if (MODE == MODE_TOPK) {
-                        if (row_ok && sc * ra >= thr) {
-                            const int col = n0 + c0 + j;
-                            if (col < a.N) {
-                                const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
-                                mad_topk_insert(bs, bi, a.k, s, a.lo_index_base + col);
-                                const double kth = bs[a.k - 1];
-                                thr = (bi[a.k - 1] < 0) ? -1.f : (float)kth - 4e-6f;
-                            }
-                        }
-                    } else if (sc > thr_pairs) {
-                        const int col = n0 + c0 + j;
                         if (col < a.N) {
                             const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
+                            mad_topk_insert(bs, bi, a.k, s, a.lo_index_base + col);
+                            const double kth = bs[a.k - 1];
+                            thr = (bi[a.k - 1] < 0) ? -1.f : (float)kth - 4e-6f;
+                        }
+                    } else {                                         // rnorm is 0 beyond N: padded columns never pass (cc > 0)
+                        const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
+                        const int p = atomicAdd((int*)my_cnt, 1);
+                        if (p < STG) {
+                            my_key[p] = key;
+                            my_dot[p] = dot;
+                        } else if (col < a.N) {                      // staging full (very dense hits): exact test right here
+                            const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
                             if (s > a.cc) {
-                                const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
-                                const int p = atomicAdd((int*)my_cnt, 1);
-                                if (p < STG) {
-                                    my_key[p] = key;
-                                    my_dot[p] = dot;
-                                } else {                             // staging full (very dense hits): straight to global
-                                    const unsigned long long gp = atomicAdd(a.count, 1ULL);
-                                    if (gp < a.cap) { a.cand_key[gp] = key; a.cand_dot[gp] = dot; }
-                                }
+                                const unsigned long long gp = atomicAdd(a.count, 1ULL);
+                                if (gp < a.cap) { a.cand_key[gp] = key; a.cand_dot[gp] = dot; }
                             }
                         }
                     }

@@ -20,6 +20,36 @@ __device__ __forceinline__ int norm50(int h, int hmax) {
     return (int)((double)h / (double)hmax * 50.0);   // np.array(h / max * 50, dtype=int32)
 }
 
+// Exact (reference-arithmetic) votes of one direction; out of line, they run for the ~0.1 % of
+// directions within 2e-5 rad of a zone edge (zone_fast returned -1).
+// Unrotated patch: float32 angles against float64 bounds (mad/Orientator.py:305-334 under NumPy 2).
+__device__ __noinline__ void vote_exact_f32(ZoneTab T, float gx, float gy, float gz, int* hist) {
+    float th = (float)atan2((double)gy, (double)gx);
+    if (th < 0.f) th = __fadd_rn(th, 6.2831855f);
+    const float sth = __fadd_rn(th, 6.2831855f);
+    const float zc = fminf(1.f, fmaxf(-1.f, gz));
+    const float ph = (float)acos((double)zc);
+    int z[2];
+    const int nzn = zones_of(T, (double)th, (double)sth, (double)ph, z);
+    if (nzn > 0) atomicAdd(&hist[z[0]], 1);
+    if (nzn > 1) atomicAdd(&hist[z[1]], 1);
+}
+// Rotated patch: float64 throughout (the rotation matrix is float64).
+__device__ __noinline__ void vote_exact_f64(ZoneTab T, const double* __restrict__ R, float gx, float gy, float gz, int* hist) {
+    const double px = gx, py = gy, pz = gz;
+    const double vx = fma(pz, R[2], fma(py, R[1], px * R[0]));
+    const double vy = fma(pz, R[5], fma(py, R[4], px * R[3]));
+    const double vz = fma(pz, R[8], fma(py, R[7], px * R[6]));
+    double th = atan2(vy, vx);
+    if (th < 0.0) th += MAD_TWO_PI;
+    const double sth = th + MAD_TWO_PI;
+    const double ph = acos(fmin(1.0, fmax(-1.0, vz)));
+    int z[2];
+    const int nzn = zones_of(T, th, sth, ph, z);
+    if (nzn > 0) atomicAdd(&hist[z[0]], 1);
+    if (nzn > 1) atomicAdd(&hist[z[1]], 1);
+}
+
 __global__ void __launch_bounds__(128)
 orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1, OctDims dims,
               const MadKeypoint* __restrict__ kp, int r, const char4* __restrict__ mask_off, int n_mask,
@@ -31,6 +61,7 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
     __shared__ int cur[128];
     __shared__ int s_main[8];
     __shared__ int s_nmain, s_hmax, s_count;
+    __shared__ ZoneFast F;
 
     const int tid = threadIdx.x;
     const int ki = blockIdx.x;
@@ -48,6 +79,7 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
     }
     if (tid < 128) { hist[tid] = 0; }
     if (tid == 0) { s_hmax = 0; s_count = 0; s_nmain = 0; }
+    zone_fast_init(&F, T);
     __syncthreads();
 
     // ---- step01 + first histogram (float32 angles against float64 bounds) ----
@@ -64,15 +96,9 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
         g.w = (m < 1e-5f) ? 0.f : 1.f;
         pv[i] = g;
         if (g.w != 0.f) {
-            float th = (float)atan2((double)g.y, (double)g.x);
-            if (th < 0.f) th = __fadd_rn(th, 6.2831855f);
-            const float sth = __fadd_rn(th, 6.2831855f);
-            const float zc = fminf(1.f, fmaxf(-1.f, g.z));
-            const float ph = (float)acos((double)zc);
-            int z[2];
-            const int nzn = zones_of(T, (double)th, (double)sth, (double)ph, z);
-            if (nzn > 0) atomicAdd(&hist[z[0]], 1);
-            if (nzn > 1) atomicAdd(&hist[z[1]], 1);
+            const int zf = zone_fast(F, g.x, g.y, g.z);
+            if (zf >= 0) atomicAdd(&hist[zf], 1);
+            else vote_exact_f32(T, g.x, g.y, g.z, hist);
         }
     }
     __syncthreads();
@@ -107,22 +133,17 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
             if (tid == 0) s_hmax = 0;
             __syncthreads();
             const double* R = r1_table + 9 * a;
-            const double r00 = R[0], r01 = R[1], r02 = R[2], r10 = R[3], r11 = R[4], r12 = R[5], r20 = R[6], r21 = R[7], r22 = R[8];
+            float rf[9];
+#pragma unroll
+            for (int q = 0; q < 9; ++q) rf[q] = (float)R[q];
             for (int i = tid; i < n_mask; i += blockDim.x) {
                 const float4 g = pv[i];
                 if (g.w == 0.f) continue;
-                const double px = g.x, py = g.y, pz = g.z;
-                const double vx = fma(pz, r02, fma(py, r01, px * r00));
-                const double vy = fma(pz, r12, fma(py, r11, px * r10));
-                const double vz = fma(pz, r22, fma(py, r21, px * r20));
-                double th = atan2(vy, vx);
-                if (th < 0.0) th += MAD_TWO_PI;
-                const double sth = th + MAD_TWO_PI;
-                const double ph = acos(fmin(1.0, fmax(-1.0, vz)));
-                int z[2];
-                const int nzn = zones_of(T, th, sth, ph, z);
-                if (nzn > 0) atomicAdd(&hist[z[0]], 1);
-                if (nzn > 1) atomicAdd(&hist[z[1]], 1);
+                const int zf = zone_fast(F, fmaf(g.z, rf[2], fmaf(g.y, rf[1], g.x * rf[0])),
+                                         fmaf(g.z, rf[5], fmaf(g.y, rf[4], g.x * rf[3])),
+                                         fmaf(g.z, rf[8], fmaf(g.y, rf[7], g.x * rf[6])));
+                if (zf >= 0) atomicAdd(&hist[zf], 1);
+                else vote_exact_f64(T, R, g.x, g.y, g.z, hist);
             }
             __syncthreads();
             if (tid < T.n_zones) atomicMax(&s_hmax, hist[tid]);

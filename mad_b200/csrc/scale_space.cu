@@ -399,48 +399,75 @@ __device__ __forceinline__ float conv_g(const ACC* win, int t, const ConvW& w) {
     return (float)a0;
 }
 
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // MODE 0: pass X (in0=f; o0=P0, o1=Q0).  MODE 1: pass Y (in0=P0, in1=Q0; o0=P01, o1=R, o2=S).
 // One thread per line, marching along the (strided) axis; consecutive threads own consecutive z,
-// so every load and store of a warp is one coalesced 128-byte line.
+// so every load and store of a warp is one coalesced 128-byte line.  Samples travel
+// global -> shared through cp.async (LDGSTS) into a private per-thread ring of D rows, PF groups
+// of T rows ahead of the arithmetic: the HBM latency is covered by ~24 rows in flight per thread
+// without spending registers on them, and no block-level barrier is needed (a thread only ever
+// reads what it copied itself).  The reflect boundary is applied when the copy is issued.
 template <int R, typename ACC, int MODE>
 __global__ void __launch_bounds__(128)
 log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__ in1, float* __restrict__ o0,
                         float* __restrict__ o1, float* __restrict__ o2, int n, long long inner,
                         long long total_lines, int seg_len, ConvW w) {
-    constexpr int T = 8, W = T + 2 * R;
+    constexpr int T = ((2 * R) % 8 == 0) ? 8 : 4, W = T + 2 * R;
+    constexpr int NA = MODE == 1 ? 2 : 1;
+    constexpr int D = 32, PF = D / T - 1;          // ring depth (rows) and groups in flight ahead
+    constexpr int G0 = 2 * R / T;                  // groups that make up the initial window
+    static_assert((2 * R) % T == 0, "window prologue must be whole groups");
+    extern __shared__ float ring[];                // [D][NA][128]
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= total_lines) return;
     const long long o = g / inner, j = g % inner;
     const long long base = o * (long long)n * inner + j;
     const int a0 = blockIdx.y * seg_len;
     const int a1 = min(n, a0 + seg_len);
+    const int q_end = a1 - a0 + 2 * R;             // samples this thread needs: q = pos - (a0 - R) in [0, q_end)
+    float* my = ring + threadIdx.x;
+    auto issue = [&](int grp) {
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const int q = grp * T + i;
+            if (q < q_end) {
+                const long long off = base + (long long)mad_reflect(a0 - R + q, n) * inner;
+                float* dst = my + ((q & (D - 1)) * NA) * 128;
+                cp_async4(dst, in0 + off);
+                if (MODE == 1) cp_async4(dst + 128, in1 + off);
+            }
+        }
+        cp_async_commit();
+    };
+    static_assert(G0 <= PF + 1, "the initial window must fit the ring");
+#pragma unroll
+    for (int grp = 0; grp <= PF; ++grp) issue(grp);         // fill the ring: groups 0 .. PF
+    cp_async_wait<PF + 1 - G0>();                           // groups 0 .. G0-1 (the initial window) have landed
     ACC wa[W];
     ACC wb[MODE == 1 ? W : 1];
 #pragma unroll
     for (int i = 0; i < 2 * R; ++i) {
-        const long long off = base + (long long)mad_reflect(a0 - R + i, n) * inner;
-        wa[i] = (ACC)__ldg(in0 + off);
-        if (MODE == 1) wb[i] = (ACC)__ldg(in1 + off);
+        wa[i] = (ACC)my[(i * NA) * 128];
+        if (MODE == 1) wb[i] = (ACC)my[(i * NA + 1) * 128];
     }
-    for (int a = a0; a < a1; a += T) {
-        float la[T], lb[MODE == 1 ? T : 1];
+#pragma unroll
+    for (int grp = PF + 1; grp <= PF + G0; ++grp) issue(grp);   // their slots are free again
+    int grp = G0;
+    for (int a = a0; a < a1; a += T, ++grp) {
+        cp_async_wait<PF>();                                 // group `grp` (the T new samples of this step) has landed
 #pragma unroll
         for (int i = 0; i < T; ++i) {
-            const int pos = a + R + i;
-            float va = 0.f, vb = 0.f;
-            if (pos <= n - 1 + R) {
-                const long long off = base + (long long)mad_reflect(pos, n) * inner;
-                va = __ldg(in0 + off);
-                if (MODE == 1) vb = __ldg(in1 + off);
-            }
-            la[i] = va;
-            if (MODE == 1) lb[i] = vb;
+            const int slot = (grp * T + i) & (D - 1);
+            wa[2 * R + i] = (ACC)my[(slot * NA) * 128];
+            if (MODE == 1) wb[2 * R + i] = (ACC)my[(slot * NA + 1) * 128];
         }
-#pragma unroll
-        for (int i = 0; i < T; ++i) {
-            wa[2 * R + i] = (ACC)la[i];
-            if (MODE == 1) wb[2 * R + i] = (ACC)lb[i];
-        }
+        issue(grp + PF + 1);                                 // refill the slots just read
 #pragma unroll
         for (int t = 0; t < T; ++t) {
             if (a + t < a1) {
@@ -458,6 +485,7 @@ log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__
             if (MODE == 1) wb[i] = wb[i + T];
         }
     }
+    cp_async_wait<0>();
 }
 
 // Pass Z (contiguous axis): rows are staged in shared memory with coalesced loads (reflect halo
@@ -561,7 +589,7 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
         const int seg_len = segs_for(inner, nx);
         dim3 grid_dim((unsigned)mad_ceil_div(inner, 128), (unsigned)mad_ceil_div(nx, seg_len));
         MAD_PROF("log_pass_x_kernel", st);
-        log_pass_strided_kernel<R, ACC, 0><<<grid_dim, 128, 0, st>>>(grid, nullptr, P0, Q0, nullptr, nx, inner, inner, seg_len, w);
+        log_pass_strided_kernel<R, ACC, 0><<<grid_dim, 128, 32 * 1 * 128 * sizeof(float), st>>>(grid, nullptr, P0, Q0, nullptr, nx, inner, inner, seg_len, w);
         MAD_LAUNCH_OK();
     }
     {
@@ -570,7 +598,7 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
         const int seg_len = segs_for(lines, ny);
         dim3 grid_dim((unsigned)mad_ceil_div(lines, 128), (unsigned)mad_ceil_div(ny, seg_len));
         MAD_PROF("log_pass_y_kernel", st);
-        log_pass_strided_kernel<R, ACC, 1><<<grid_dim, 128, 0, st>>>(P0, Q0, P01, Rr, S, ny, inner, lines, seg_len, w);
+        log_pass_strided_kernel<R, ACC, 1><<<grid_dim, 128, 32 * 2 * 128 * sizeof(float), st>>>(P0, Q0, P01, Rr, S, ny, inner, lines, seg_len, w);
         MAD_LAUNCH_OK();
     }
     {

@@ -356,8 +356,8 @@ def test_entries_above_255_use_the_fp16_kernel(P):
     from mad_b200._lib import MadError
     lo = synth.synthetic_descriptors(300, 31)
     hi = synth.synthetic_descriptors(200, 32, noisy_copy_of=lo)
-    lo[:, :16] *= 5                                              # entries up to 320
-    hi[:, :16] *= 5
+    lo[:, :16] *= 9                                              # entries of 16-bin blocks reach ~40: up to ~360
+    hi[:, :16] *= 9
     assert P.DescriptorSet(lo).max_entry > 255
     r = P.match_threshold(hi, lo, 0.5)
     r1 = P.match_threshold(hi, lo, 0.5, impl=1)
