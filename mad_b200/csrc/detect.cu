@@ -82,30 +82,52 @@ __device__ double sym3_max_eig(const float Hf[3][3]) {
     return q + 2.0 * p * cos(phi);
 }
 
+// Phase 1: one thread per interior voxel (blockIdx.y = x plane, one 32-bit divide for (y, z)).
+// Voxels above the threshold that equal their 3x3x3 maximum are appended as RAW candidates
+// (accepted = -1) with one atomicAdd each -- they are rare (thousands per map).
 __global__ void __launch_bounds__(256)
-detect_kernel(const float* __restrict__ L, int nx, int ny, int nz, int oct, int border, float thr,
-              MadKeypoint* __restrict__ cand, int cap, int* __restrict__ count) {
-    const int ix = nx - 2 * border, iy = ny - 2 * border, iz = nz - 2 * border;
-    const long long total = (long long)ix * iy * iz;
+detect_peaks_kernel(const float* __restrict__ L, int nx, int ny, int nz, int oct, int border, float thr,
+                    MadKeypoint* __restrict__ cand, int cap, int* __restrict__ count) {
+    const int iy = ny - 2 * border, iz = nz - 2 * border;
+    const unsigned plane = (unsigned)iy * (unsigned)iz;
+    const unsigned p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= plane) return;
+    const int x = (int)blockIdx.y + border;
+    const int yy = (int)(p / (unsigned)iz);
+    const int y = yy + border, z = (int)(p - (unsigned)yy * (unsigned)iz) + border;
     const long long sy = nz, sx = (long long)ny * nz;
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const int z = (int)(g % iz) + border;
-        const long long t = g / iz;
-        const int y = (int)(t % iy) + border;
-        const int x = (int)(t / iy) + border;
-        const long long c = x * sx + y * sy + z;
-        const float v = __ldg(L + c);
-        if (!(v > thr)) continue;
-        bool is_max = true;
-        for (int dx = -1; dx <= 1 && is_max; ++dx)
-            for (int dy = -1; dy <= 1 && is_max; ++dy) {
-                const float* row = L + c + dx * sx + dy * sy;
-                if (__ldg(row - 1) > v || __ldg(row) > v || __ldg(row + 1) > v) is_max = false;
-            }
-        if (!is_max) continue;
+    const long long c = x * sx + y * sy + z;
+    const float v = __ldg(L + c);
+    if (!(v > thr)) return;
+    for (int dx = -1; dx <= 1; ++dx)
+        for (int dy = -1; dy <= 1; ++dy) {
+            const float* row = L + c + dx * sx + dy * sy;
+            if (__ldg(row - 1) > v || __ldg(row) > v || __ldg(row + 1) > v) return;
+        }
+    const int slot = atomicAdd(count, 1);
+    if (slot < cap) {
+        MadKeypoint k;
+        k.vox[0] = x; k.vox[1] = y; k.vox[2] = z;
+        k.oct = oct;
+        k.off[0] = k.off[1] = k.off[2] = 0.f;
+        k.val = v;
+        k.peak[0] = x; k.peak[1] = y; k.peak[2] = z;
+        k.accepted = -1;
+        cand[slot] = k;
+    }
+}
 
-        // ---- check_localize (float32 arithmetic as NumPy 2 performs it) ----
+// Phase 2: one thread per raw candidate of this octave: check_localize (float32 arithmetic as
+// NumPy 2 performs it, mad/Detector.py:53-123).
+__global__ void __launch_bounds__(128)
+detect_refine_kernel(const float* __restrict__ L, int nx, int ny, int nz, int oct,
+                     MadKeypoint* __restrict__ cand, int cap, const int* __restrict__ count) {
+    const long long sy = nz, sx = (long long)ny * nz;
+    const int n = min(*count, cap);
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        MadKeypoint k = cand[i];
+        if (k.accepted != -1 || k.oct != oct) continue;
+        const int x = k.peak[0], y = k.peak[1], z = k.peak[2];
         int px = x, py = y, pz = z;
         float off[3] = {0.f, 0.f, 0.f};
         float H[3][3];
@@ -138,18 +160,10 @@ detect_kernel(const float* __restrict__ L, int nx, int ny, int nz, int oct, int 
         }
         bool ok = converged && !singular;
         if (ok && sym3_max_eig(H) > 0.0) ok = false;
-
-        const int slot = atomicAdd(count, 1);
-        if (slot < cap) {
-            MadKeypoint k;
-            k.vox[0] = ok ? px : x; k.vox[1] = ok ? py : y; k.vox[2] = ok ? pz : z;
-            k.oct = oct;
-            k.off[0] = ok ? off[0] : 0.f; k.off[1] = ok ? off[1] : 0.f; k.off[2] = ok ? off[2] : 0.f;
-            k.val = v;
-            k.peak[0] = x; k.peak[1] = y; k.peak[2] = z;
-            k.accepted = ok ? 1 : 0;
-            cand[slot] = k;
-        }
+        k.vox[0] = ok ? px : x; k.vox[1] = ok ? py : y; k.vox[2] = ok ? pz : z;
+        k.off[0] = ok ? off[0] : 0.f; k.off[1] = ok ? off[1] : 0.f; k.off[2] = ok ? off[2] : 0.f;
+        k.accepted = ok ? 1 : 0;
+        cand[i] = k;
     }
 }
 
@@ -208,10 +222,17 @@ extern "C" int mad_detect(const float* log_grid, int nx, int ny, int nz, int oct
     MAD_CHECK_ARG(log_grid && cand && count && cap > 0 && border >= 1);
     MAD_CHECK_ARG((long long)nx * ny * nz < (1ll << 32));
     if (nx <= 2 * border || ny <= 2 * border || nz <= 2 * border) return MAD_OK;  // nothing can be detected
-    const long long total = (long long)(nx - 2 * border) * (ny - 2 * border) * (nz - 2 * border);
-    const int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 32);
-    MAD_PROF("detect_kernel", stream);
-    detect_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(log_grid, nx, ny, nz, oct, border, threshold, cand, cap, count);
+    const int ix = nx - 2 * border, iy = ny - 2 * border, iz = nz - 2 * border;
+    MAD_CHECK_ARG(ix <= 65535);
+    cudaStream_t st = (cudaStream_t)stream;
+    {
+        dim3 grid_dim((unsigned)mad_ceil_div((long long)iy * iz, 256), (unsigned)ix);
+        MAD_PROF("detect_peaks_kernel", st);
+        detect_peaks_kernel<<<grid_dim, 256, 0, st>>>(log_grid, nx, ny, nz, oct, border, threshold, cand, cap, count);
+        MAD_LAUNCH_OK();
+    }
+    MAD_PROF("detect_refine_kernel", st);
+    detect_refine_kernel<<<mad_sm_count(), 128, 0, st>>>(log_grid, nx, ny, nz, oct, cand, cap, count);
     MAD_LAUNCH_OK();
     return MAD_OK;
 }

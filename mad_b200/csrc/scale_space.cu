@@ -488,82 +488,99 @@ log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__
     cp_async_wait<0>();
 }
 
-// Pass Z (contiguous axis): rows are staged in shared memory with coalesced loads (reflect halo
-// applied while staging); a thread produces T consecutive outputs of one row from a register
-// window converted once to the accumulation type, one array after the other.
+// Pass Z (contiguous axis).  Persistent CTAs walk over batches of rows; the three input rows of the
+// NEXT batch travel global -> shared with cp.async (4-byte copies: rows of an odd-length grid are
+// only 4-byte aligned; the reflect halo is applied by the copy's source index) while the current
+// batch is being convolved, so the HBM latency is hidden behind the FP64 work.  A thread produces
+// T consecutive outputs of one row from a register window converted once to the accumulation
+// type, one input array after the other; results are staged in shared memory and written as
+// whole rows (coalesced).
 template <int R, typename ACC>
 __global__ void __launch_bounds__(128)
 log_pass_z_kernel(const float* __restrict__ P01, const float* __restrict__ Rr, const float* __restrict__ S,
                   float* __restrict__ log_out, float* __restrict__ gauss_out, int nz, long long n_rows,
-                  int rows_per_cta, int rs_in, int rs_out, float scale, ConvW w) {
+                  int rows_per_cta, int rs_in, int rs_out, long long n_batches, float scale, ConvW w) {
     constexpr int T = 8, W = T + 2 * R;
     extern __shared__ __align__(16) float zsm[];
-    float* sin0 = zsm;
-    float* sin1 = sin0 + (size_t)rows_per_cta * rs_in;
-    float* sin2 = sin1 + (size_t)rows_per_cta * rs_in;
-    float* sout0 = sin2 + (size_t)rows_per_cta * rs_in;
+    const size_t in_buf = (size_t)3 * rows_per_cta * rs_in;          // floats per input buffer
+    float* sout0 = zsm + 2 * in_buf;
     float* sout1 = sout0 + (size_t)rows_per_cta * rs_out;
-    const long long row0 = (long long)blockIdx.x * rows_per_cta;
-    const int rows = (int)min((long long)rows_per_cta, n_rows - row0);
     const int tid = threadIdx.x;
-    for (int r = 0; r < rows; ++r) {
-        const long long gb = (row0 + r) * nz;
-        for (int t = tid; t < rs_in; t += blockDim.x) {
-            float a = 0.f, b = 0.f, c = 0.f;
-            if (t < nz + 2 * R) {
-                const int z = mad_reflect(t - R, nz);
-                a = __ldg(P01 + gb + z);
-                b = __ldg(Rr + gb + z);
-                c = __ldg(S + gb + z);
+    const int halo_len = nz + 2 * R;
+    auto issue = [&](long long batch, int buf) {
+        if (batch < n_batches) {
+            const long long row0 = batch * rows_per_cta;
+            const int rows = (int)min((long long)rows_per_cta, n_rows - row0);
+            float* d0 = zsm + buf * in_buf;
+            for (int r = 0; r < rows; ++r) {
+                const long long gb = (row0 + r) * nz;
+                for (int t = tid; t < halo_len; t += 128) {
+                    const long long src = gb + mad_reflect(t - R, nz);
+                    float* d = d0 + r * rs_in + t;
+                    cp_async4(d, P01 + src);
+                    cp_async4(d + (size_t)rows_per_cta * rs_in, Rr + src);
+                    cp_async4(d + (size_t)2 * rows_per_cta * rs_in, S + src);
+                }
             }
-            sin0[r * rs_in + t] = a;
-            sin1[r * rs_in + t] = b;
-            sin2[r * rs_in + t] = c;
         }
-    }
-    __syncthreads();
+        cp_async_commit();
+    };
     const int n_chunks = (nz + T - 1) / T;
-    for (int it = tid; it < rows * n_chunks; it += blockDim.x) {
-        const int r = it / n_chunks, c = it % n_chunks;
-        const int z0 = c * T;
-        ACC win[W];
-        auto load_window = [&](const float* src) {
-            const float4* p = reinterpret_cast<const float4*>(src + r * rs_in + z0);
+    int buf = 0;
+    issue(blockIdx.x, 0);
+    for (long long batch = blockIdx.x; batch < n_batches; batch += gridDim.x, buf ^= 1) {
+        issue(batch + gridDim.x, buf ^ 1);
+        cp_async_wait<1>();                                           // this batch's rows have landed
+        __syncthreads();
+        const long long row0 = batch * rows_per_cta;
+        const int rows = (int)min((long long)rows_per_cta, n_rows - row0);
+        const float* sin0 = zsm + buf * in_buf;
+        const float* sin1 = sin0 + (size_t)rows_per_cta * rs_in;
+        const float* sin2 = sin1 + (size_t)rows_per_cta * rs_in;
+        for (int it = tid; it < rows * n_chunks; it += blockDim.x) {
+            const int r = it / n_chunks, c = it % n_chunks;
+            const int z0 = c * T;
+            ACC win[W];
+            auto load_window = [&](const float* src) {
+                const float4* p = reinterpret_cast<const float4*>(src + r * rs_in + z0);
 #pragma unroll
-            for (int q = 0; q < W / 4; ++q) {
-                const float4 v = p[q];
-                win[4 * q] = (ACC)v.x; win[4 * q + 1] = (ACC)v.y; win[4 * q + 2] = (ACC)v.z; win[4 * q + 3] = (ACC)v.w;
-            }
-        };
-        float gs[T], t3[T], t2[T], t1[T];
-        load_window(sin0);
+                for (int q = 0; q < W / 4; ++q) {
+                    const float4 v = p[q];
+                    win[4 * q] = (ACC)v.x; win[4 * q + 1] = (ACC)v.y; win[4 * q + 2] = (ACC)v.z; win[4 * q + 3] = (ACC)v.w;
+                }
+            };
+            float gs[T], t3[T], t2[T], t1[T];
+            load_window(sin0);
 #pragma unroll
-        for (int t = 0; t < T; ++t) conv_both<R, ACC>(win, t, w, gs[t], t3[t]);
-        load_window(sin1);
+            for (int t = 0; t < T; ++t) conv_both<R, ACC>(win, t, w, gs[t], t3[t]);
+            load_window(sin1);
 #pragma unroll
-        for (int t = 0; t < T; ++t) t2[t] = conv_g<R, ACC>(win, t, w);
-        load_window(sin2);
+            for (int t = 0; t < T; ++t) t2[t] = conv_g<R, ACC>(win, t, w);
+            load_window(sin2);
 #pragma unroll
-        for (int t = 0; t < T; ++t) t1[t] = conv_g<R, ACC>(win, t, w);
+            for (int t = 0; t < T; ++t) t1[t] = conv_g<R, ACC>(win, t, w);
 #pragma unroll
-        for (int t = 0; t < T; ++t) {
-            const float lap = __fadd_rn(__fadd_rn(t1[t], t2[t]), t3[t]);
-            float m = __fmul_rn(-lap, scale);
-            if (m < 0.f) m = 0.f;
-            if (z0 + t < nz) {
-                sout0[r * rs_out + z0 + t] = m;
-                sout1[r * rs_out + z0 + t] = gs[t];
+            for (int t = 0; t < T; ++t) {
+                const float lap = __fadd_rn(__fadd_rn(t1[t], t2[t]), t3[t]);
+                float m = __fmul_rn(-lap, scale);
+                if (m < 0.f) m = 0.f;
+                if (z0 + t < nz) {
+                    sout0[r * rs_out + z0 + t] = m;
+                    sout1[r * rs_out + z0 + t] = gs[t];
+                }
             }
         }
-    }
-    __syncthreads();
-    for (int r = 0; r < rows; ++r) {
-        const long long gb = (row0 + r) * nz;
-        for (int t = tid; t < nz; t += blockDim.x) {
-            log_out[gb + t] = sout0[r * rs_out + t];
-            gauss_out[gb + t] = sout1[r * rs_out + t];
+        __syncthreads();
+        for (int r = 0; r < rows; ++r) {
+            const long long gb = (row0 + r) * nz;
+            for (int t = tid; t < nz; t += blockDim.x) {
+                log_out[gb + t] = sout0[r * rs_out + t];
+                gauss_out[gb + t] = sout1[r * rs_out + t];
+            }
         }
+        // the next iteration's barrier (after its wait) orders these reads of sout before its writes
     }
+    cp_async_wait<0>();
 }
 
 extern "C" size_t mad_log_gauss_workspace_bytes(int nx, int ny, int nz) {
@@ -606,16 +623,28 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
         const int n_chunks = (nz + 7) / 8;
         const int rs_in = (n_chunks * 8 + 2 * R + 3) / 4 * 4;
         const int rs_out = (nz + 3) / 4 * 4;
-        const size_t row_bytes = (size_t)(3 * rs_in + 2 * rs_out) * sizeof(float);
-        int rows = (int)std::max<long long>(1, std::min<long long>(mad_ceil_div(256, n_chunks), (long long)(48 * 1024 / row_bytes)));
+        const size_t row_bytes = (size_t)(2 * 3 * rs_in + 2 * rs_out) * sizeof(float);   // double-buffered inputs + outputs
+        // rows per batch: the value (within ~72 KB of shared memory, 3 CTAs per SM) that leaves the
+        // fewest idle threads in the last pass over rows x chunks
+        const int max_rows = (int)std::max<size_t>(1, std::min<size_t>(32, (72 * 1024) / row_bytes));
+        int rows = 1;
+        double best_eff = -1.0;
+        for (int r = 1; r <= max_rows; ++r) {
+            const long long work = (long long)r * n_chunks;
+            const double eff = (double)work / (double)(mad_ceil_div(work, 128) * 128);
+            if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && r > rows)) { best_eff = std::max(best_eff, eff); rows = r; }
+        }
         const size_t smem = rows * row_bytes;
         if (smem > 200 * 1024) {
             mad_set_error("mad_log_gauss: z extent %d too long for the shared-memory row stage", nz);
             return MAD_ERR_ARG;
         }
         MAD_CUDA(cudaFuncSetAttribute(log_pass_z_kernel<R, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        const long long n_batches = mad_ceil_div(n_rows, rows);
+        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(216 * 1024) / std::max<size_t>(smem, 1)));
+        const unsigned grid_z = (unsigned)std::min<long long>(n_batches, (long long)sms * ctas_per_sm);
         MAD_PROF("log_pass_z_kernel", st);
-        log_pass_z_kernel<R, ACC><<<(unsigned)mad_ceil_div(n_rows, rows), 128, smem, st>>>(P01, Rr, S, log_out, gauss_out, nz, n_rows, rows, rs_in, rs_out, scale, w);
+        log_pass_z_kernel<R, ACC><<<grid_z, 128, smem, st>>>(P01, Rr, S, log_out, gauss_out, nz, n_rows, rows, rs_in, rs_out, n_batches, scale, w);
         MAD_LAUNCH_OK();
     }
     return MAD_OK;
@@ -662,30 +691,34 @@ __device__ __forceinline__ float grad_axis(const float* __restrict__ f, long lon
     return __fmul_rn(__fsub_rn(__ldg(f + c + stride), __ldg(f + c - stride)), 0.5f);
 }
 
+// One thread per voxel; blockIdx.y = x plane, blockIdx.x*256 + tid = index inside the (y, z) plane,
+// so the only division is one 32-bit divide by nz.  Loads of a warp are coalesced rows of the
+// x-1 / x+1 planes and the y-1 / y+1 rows (the z neighbours come from L1); the store is one
+// 16-byte (gx, gy, gz, 0) per voxel, 512 contiguous bytes per warp.
 __global__ void __launch_bounds__(256)
-gradient_kernel(const float* __restrict__ f, int nx, int ny, int nz, float4* __restrict__ grad, long long total) {
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        const int z = (int)(g % nz);
-        const long long t = g / nz;
-        const int y = (int)(t % ny);
-        const int x = (int)(t / ny);
-        float4 v;
-        v.x = grad_axis(f, g, x, nx, (long long)ny * nz);
-        v.y = grad_axis(f, g, y, ny, nz);
-        v.z = grad_axis(f, g, z, nz, 1);
-        v.w = 0.f;
-        grad[g] = v;
-    }
+gradient_kernel(const float* __restrict__ f, int nx, int ny, int nz, float4* __restrict__ grad) {
+    const unsigned plane = (unsigned)ny * (unsigned)nz;
+    const unsigned p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= plane) return;
+    const int x = blockIdx.y;
+    const int y = (int)(p / (unsigned)nz);
+    const int z = (int)(p - (unsigned)y * (unsigned)nz);
+    const long long c = (long long)x * plane + p;
+    float4 v;
+    v.x = grad_axis(f, c, x, nx, (long long)plane);
+    v.y = grad_axis(f, c, y, ny, nz);
+    v.z = grad_axis(f, c, z, nz, 1);
+    v.w = 0.f;
+    grad[c] = v;
 }
 
 extern "C" int mad_gradient(const float* gauss, int nx, int ny, int nz, float* grad4, void* stream) {
     MAD_CHECK_ARG(gauss && grad4 && nx >= 2 && ny >= 2 && nz >= 2);
     MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad4) & 15) == 0);
-    const long long total = (long long)nx * ny * nz;
-    const int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 32);
+    MAD_CHECK_ARG(nx <= 65535 && (long long)ny * nz < (1LL << 31));
+    dim3 grid_dim((unsigned)mad_ceil_div((long long)ny * nz, 256), (unsigned)nx);
     MAD_PROF("gradient_kernel", stream);
-    gradient_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(gauss, nx, ny, nz, reinterpret_cast<float4*>(grad4), total);
+    gradient_kernel<<<grid_dim, 256, 0, (cudaStream_t)stream>>>(gauss, nx, ny, nz, reinterpret_cast<float4*>(grad4));
     MAD_LAUNCH_OK();
     return MAD_OK;
 }
