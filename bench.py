@@ -234,27 +234,31 @@ def main():
     grid_d = grid_pin.to(dev)
     exact = bool(args.exact)
 
-    # component descriptor sets: resident in HBM before the timed region (MaD caches them: dsc_db/)
+    # component descriptor sets: resident in HBM before the timed region (MaD caches them: dsc_db/).
+    # All components are stacked into ONE hi set, so one matching launch per step serves the six
+    # subunits (pairs carry the global hi row; comp_offs maps rows back to components).
     comp_sets = []
     for c in comps_h:
         _, _, _, dsc = P.describe_struct(c, exact_f64=exact)
         comp_sets.append(P.DescriptorSet(dsc))
+    hi_all, comp_offs = P.concat_sets(comp_sets)
     torch.cuda.synchronize()
+    stage = P.HostStage()
 
     def step_device():
         sp, kp, ori, dsc = P.describe_struct(grid_d, exact_f64=exact)
         lo = P.DescriptorSet(dsc)
-        pairs = [P.match_threshold(hi, lo, 0.6, impl=args.match_impl) for hi in comp_sets]
-        return sp, kp, ori, dsc, pairs
+        pairs = P.match_threshold(hi_all, lo, 0.6, impl=args.match_impl)
+        return sp, kp, ori, dsc, [pairs]
 
     def step_e2e():
         g = grid_pin.to(dev, non_blocking=True)
         sp, kp, ori, dsc = P.describe_struct(g, exact_f64=exact)
+        out = [stage.fetch("dsc", dsc), stage.fetch("kp", kp.table[:len(kp)]), stage.fetch("ori", ori.table[:len(ori)])]
         lo = P.DescriptorSet(dsc)
-        out = [dsc.cpu(), kp.table[:len(kp)].cpu(), ori.table[:len(ori)].cpu()]
-        for hi in comp_sets:
-            ph, pl, sc = P.match_threshold(hi, lo, 0.6, impl=args.match_impl)
-            out += [ph.cpu(), pl.cpu(), sc.cpu()]
+        ph, pl, sc = P.match_threshold(hi_all, lo, 0.6, impl=args.match_impl)
+        out += [stage.fetch("ph", ph), stage.fetch("pl", pl), stage.fetch("sc", sc)]
+        stage.sync()
         return out
 
     def barrier():
@@ -325,44 +329,75 @@ def main():
     pk_path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    hbm_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md 6.65 TB/s)"
+    bf16_peak = float(peaks.get("bf16_tflops", 1590.0))
+    tc_src = ("2 x measured bf16 burst (MEASURED_PEAKS.json bf16_tflops): uint8 x uint8 -> int32 tcgen05.mma.kind::i8 "
+              "runs at twice the 16-bit rate" if "bf16_tflops" in peaks else "2 x fallback bf16 1.59 PFLOP/s")
 
     by_name = {}
     for nm, t in recs:
         by_name.setdefault(nm, []).append(t)
     total_kernel_ms = sum(sum(v) for v in by_name.values())
     kernels = sorted(((nm, sum(v), len(v)) for nm, v in by_name.items()), key=lambda x: -x[1])
-    top_name, top_ms, top_n = kernels[0]
-    # launches of the top kernel alternate octave 0 / octave 1 (two per step): the octave-0 launches
-    # dominate; report the roofline on those (largest duration half), bytes for V0.
-    top_durs = sorted(by_name[top_name], reverse=True)
-    per_step = max(1, top_n // args.steps)
-    big = top_durs[: max(1, top_n // per_step)] if per_step > 1 else top_durs
-    avg_ms = float(np.mean(big))
-    ctx = {"V_cur": V0, "V0": V0, "V1": V1, "V_in": n_vox}
-    ab = algorithmic_bytes(top_name, ctx)
-    if top_name == "orient_kernel":
-        ab = 58956 * K
-    elif top_name == "describe_kernel":
-        ab = 51200 * D
+
+    # algorithmic bytes / ops of ONE launch of each kernel (SURVEY 8d convention).
+    # Kernels launched once per octave: the octave-0 (up grid) launch dominates; its duration is the
+    # larger of the two per step and its bytes are those of V0.
+    M_hi = hi_all.rows
+    alg = {
+        "log_pass_x_kernel": ("hbm", 12 * V0), "log_pass_y_kernel": ("hbm", 20 * V0), "log_pass_z_kernel": ("hbm", 20 * V0),
+        "gradient_kernel": ("hbm", 16 * V0 + 4 * V0), "detect_peaks_kernel": ("hbm", 4 * V0),
+        "spline_up_z_kernel": ("hbm", 4 * V1 + 8 * 2 * V1), "spline_up_x_kernel": ("hbm", 8 * 2 * V1 + 8 * 4 * V1),
+        "spline_up_y_kernel": ("hbm", 8 * 4 * V1 + 4 * V0), "pad3d_kernel": ("hbm", 4 * n_vox + 4 * V1),
+        "orient_kernel": ("hbm", 58956 * K), "describe_kernel": ("hbm", 51200 * D),
+        "match_u8_pairs_kernel": ("tensor", 2.0 * M_hi * D * 1024),
+    }
+    traffic = {}
+    tr_path = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path))
+
+    def kernel_roofline(name):
+        if name not in alg or name not in by_name:
+            return None
+        bound, amount = alg[name]
+        durs = sorted(by_name[name], reverse=True)
+        per_step = max(1, len(durs) // args.steps)
+        big = durs[: max(1, len(durs) // per_step)]          # the octave-0 launches (one per step)
+        avg_ms = float(np.mean(big))
+        if bound == "hbm":
+            achieved, pk, unit, src = amount / (avg_ms * 1e-3) / 1e9, hbm_peak, "GB/s", hbm_src
+        else:
+            achieved, pk, unit, src = amount / (avg_ms * 1e-3) / 1e12, 2.0 * bf16_peak, "TFLOP/s", tc_src
+        return {"bound": bound, "kernel": name, "achieved": achieved, "peak": pk, "unit": unit, "frac": achieved / pk,
+                "traffic": traffic.get(name), "peak_source": src, "algorithmic_per_launch": amount,
+                "avg_launch_ms": avg_ms, "share_of_kernel_time": sum(durs) / total_kernel_ms}
+
     roofline = None
-    if ab:
-        achieved = ab / (avg_ms * 1e-3) / 1e9
-        roofline = {"bound": "hbm", "kernel": top_name, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                    "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": ab, "avg_launch_ms": avg_ms,
-                    "share_of_kernel_time": top_ms / total_kernel_ms}
+    for nm, _, _ in kernels:                                  # dominant kernel = largest share with a model
+        roofline = kernel_roofline(nm)
+        if roofline:
+            break
+    per_kernel = {}
+    for nm, _, _ in kernels:
+        r = kernel_roofline(nm)
+        if r:
+            per_kernel[nm] = {"ms": round(r["avg_launch_ms"], 4), "achieved": round(r["achieved"], 1), "unit": r["unit"],
+                              "frac": round(r["frac"], 4)}
     map_bytes = 36 * (V0 + V1) + 58956 * K + 51200 * D
     step_ms = ms / args.steps
+    describe_ms = sum(sum(v) for k, v in by_name.items() if "match" not in k and "pairs" not in k and "dsc_prepare" not in k
+                      and k != "cub_radix_sort_pairs") / args.steps
+    match_ms = total_kernel_ms / args.steps - describe_ms
     value = world * n_vox / (step_ms * 1e-3)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32 storage, f64 line accumulation" if exact else "f32",
+        "vs_baseline": None, "dtype": "f32 grids, f64 line accumulation, u8 x u8 -> s32 matching" if exact else "f32",
         "data": "synthetic",
         "config": {"workload": workload_name(), "grids": {"up": list(dims[0]), "base": list(dims[1])},
-                   "keypoints": K, "oriented_features": D, "pairs": n_pairs,
+                   "keypoints": K, "oriented_features": D, "component_descriptors": M_hi, "pairs": n_pairs,
                    "parallelism": "1 map per GPU, no collective" if world > 1 else "1 GPU",
                    "l2": "no explicit flush: per-step working set %.1f GB >> 126 MB L2" % (40.0 * (V0 + V1) / 1e9),
                    "exact_f64": exact},
@@ -372,17 +407,21 @@ def main():
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,
-        "path_roofline": {"algorithmic_bytes_per_map": map_bytes, "achieved": map_bytes / (step_ms * 1e-3) / 1e9,
-                          "peak": peak, "unit": "GB/s", "frac": map_bytes / (step_ms * 1e-3) / 1e9 / peak},
-        "matches_per_s": sum(h.rows for h in comp_sets) * D / (sum(sum(v) for k, v in by_name.items() if "match" in k) / args.steps * 1e-3 + 1e-12),
+        "path_roofline": {"algorithmic_bytes_per_map": map_bytes, "describe_kernels_ms": describe_ms,
+                          "achieved": map_bytes / (describe_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": map_bytes / (describe_ms * 1e-3) / 1e9 / hbm_peak},
+        "describe_voxels_per_s": world * n_vox / (describe_ms * 1e-3),
+        "matches_per_s": world * M_hi * D / (match_ms * 1e-3 + 1e-12),
+        "per_kernel": per_kernel,
         "kernels_ms_per_step": {nm: round(t / args.steps, 4) for nm, t, _ in kernels},
     }
     if not args.no_cpu_baseline and world == 1:
         procs = 1
         v, s_per, info = cpu_run(grid_h, C2["voxelsp"], procs, 1, 0)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": procs, "kind": "port",
-                                "sample": "one %d^3 occupancy-matched crop of the same map (K=%d, D=%d), oracle/mad_oracle.py "
-                                          "(vectorised NumPy/SciPy port; the reference itself is ~10x slower, BASELINE.md)"
+                                "sample": "one %d^3 occupancy-matched crop of the same map (K=%d, D=%d) through describe + match, "
+                                          "oracle/mad_oracle.py (vectorised NumPy/SciPy port, bit-exact with the reference on the "
+                                          "fixtures; the reference itself is ~10x slower, BASELINE.md)"
                                           % (CPU_SAMPLE_SIDE, info[0][1], info[0][2]),
                                 "seconds": s_per}
     print(json.dumps(line))

@@ -91,30 +91,62 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
         return;
     }
 
-    for (int sidx = tid; sidx < total; sidx += blockDim.x) {
-        const int k = sidx % side, j = (sidx / side) % side, i = sidx / (side * side);
-        const double lx = u0 + du * i, ly = u0 + du * j, lz = u0 + du * k;
-        const double px = ((lx * Ri[0] + ly * Ri[1]) + lz * Ri[2]) + cx;
-        const double py = ((lx * Ri[3] + ly * Ri[4]) + lz * Ri[5]) + cy;
-        const double pz = ((lx * Ri[6] + ly * Ri[7]) + lz * Ri[8]) + cz;
-        const int ix = nearest_idx(px, nx), iy = nearest_idx(py, ny), iz = nearest_idx(pz, nz);
-        float4 g = __ldg(grad + ((long long)ix * ny + iy) * nz + iz);
-        const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
-        if (m < 1e-5f) continue;                    // zone -1: never counted (:190)
-        if (m > 1e-12f) {
-            g.x = __fdiv_rn(g.x, m);
-            g.y = __fdiv_rn(g.y, m);
-            g.z = __fdiv_rn(g.z, m);
-        }
-        // float32 classification; directions within 2e-5 rad of a zone edge take the exact path
-        int zone = zone_fast(F, (g.x * Rmf[0] + g.y * Rmf[1]) + g.z * Rmf[2],
-                             (g.x * Rmf[3] + g.y * Rmf[4]) + g.z * Rmf[5],
-                             (g.x * Rmf[6] + g.y * Rmf[7]) + g.z * Rmf[8]);
-        if (zone < 0) zone = zone_exact_dsc(T, rf_table + tab, g.x, g.y, g.z);
-        const int bx = (i >= c1) + (i >= c2) + (i >= c3);
+    // A thread owns one (j, k) column of the lattice and walks along i (blockDim = side^2 when
+    // side = 16): the j / k terms of the coordinate sums and the y / z sub-block are per-thread
+    // constants.  Samples are handled in batches of GB: all gathers of a batch are issued before any
+    // is consumed, and every phase is a separate branch-free loop over the batch so that the GB
+    // dependency chains (normalise, rotate, atan2f, zone) interleave in the pipeline.
+    constexpr int GB = 4;
+    const int plane = side * side;
+    for (int c = tid; c < plane; c += blockDim.x) {
+        const int k = c % side, j = c / side;
+        const double ly = u0 + du * j, lz = u0 + du * k;
+        const double ay0 = ly * Ri[1], ay1 = ly * Ri[4], ay2 = ly * Ri[7];
+        const double az0 = lz * Ri[2], az1 = lz * Ri[5], az2 = lz * Ri[8];
         const int by = (j >= c1) + (j >= c2) + (j >= c3);
         const int bz = (k >= c1) + (k >= c2) + (k >= c3);
-        atomicAdd(&cnt[(16 * by + 4 * bx + bz) * T.n_zones + zone], 1);
+        const int bin_jk = (16 * by + bz) * T.n_zones;
+        for (int i0 = 0; i0 < side; i0 += GB) {
+            float4 gv[GB];
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                const int i = min(i0 + u, side - 1);
+                const double lx = u0 + du * i;
+                const double px = ((lx * Ri[0] + ay0) + az0) + cx;
+                const double py = ((lx * Ri[3] + ay1) + az1) + cy;
+                const double pz = ((lx * Ri[6] + ay2) + az2) + cz;
+                const int ix = nearest_idx(px, nx), iy = nearest_idx(py, ny), iz = nearest_idx(pz, nz);
+                gv[u] = __ldg(grad + ((long long)ix * ny + iy) * nz + iz);
+            }
+            float vx[GB], vy[GB], vz[GB], gx[GB], gy[GB], gz[GB];
+            bool valid[GB];
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                const float4 g = gv[u];
+                const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
+                valid[u] = (i0 + u < side) && !(m < 1e-5f);     // m < 1e-5: zone -1, never counted (:190)
+                const float d = (m > 1e-12f) ? m : 1.f;         // normalise where m > 1e-12 (:160-163)
+                gx[u] = __fdiv_rn(g.x, d);
+                gy[u] = __fdiv_rn(g.y, d);
+                gz[u] = __fdiv_rn(g.z, d);
+                vx[u] = (gx[u] * Rmf[0] + gy[u] * Rmf[1]) + gz[u] * Rmf[2];
+                vy[u] = (gx[u] * Rmf[3] + gy[u] * Rmf[4]) + gz[u] * Rmf[5];
+                vz[u] = (gx[u] * Rmf[6] + gy[u] * Rmf[7]) + gz[u] * Rmf[8];
+            }
+            int zone[GB];
+#pragma unroll
+            for (int u = 0; u < GB; ++u) zone[u] = zone_fast(F, vx[u], vy[u], vz[u]);
+#pragma unroll
+            for (int u = 0; u < GB; ++u) {
+                if (valid[u]) {
+                    // directions within 2e-5 rad of a zone edge take the exact float64 path
+                    if (zone[u] < 0) zone[u] = zone_exact_dsc(T, rf_table + tab, gx[u], gy[u], gz[u]);
+                    const int i = i0 + u;
+                    const int bx = (i >= c1) + (i >= c2) + (i >= c3);
+                    atomicAdd(&cnt[bin_jk + 4 * bx * T.n_zones + zone[u]], 1);
+                }
+            }
+        }
     }
     __syncthreads();
     for (int q = tid; q < MAD_DSC_LEN; q += blockDim.x) out[q] = (int16_t)cnt[q];

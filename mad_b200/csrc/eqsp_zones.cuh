@@ -91,22 +91,24 @@ __device__ __forceinline__ void zone_fast_init(ZoneFast* F, const ZoneTab& T) {
 }
 
 // (vx, vy, vz): unit direction in float32.  Returns the zone, or -1 if the exact test must decide.
+// Straight-line code (selects, no branches) so that several independent samples of one thread
+// interleave in the pipeline.
 __device__ __forceinline__ int zone_fast(const ZoneFast& F, float vx, float vy, float vz) {
-    int b = -1;
-    for (int k = 0; k < F.n_belts; ++k)
-        if (vz < F.vz_hi[k] && vz > F.vz_lo[k]) { b = k; break; }
-    if (b < 0) return -1;
+    // belts are contiguous and descending in vz: the belt is the number of upper bounds above vz
+    int cntb = 0;
+    for (int k = 0; k < F.n_belts; ++k) cntb += (vz < F.vz_hi[k]) ? 1 : 0;
+    const int b = max(cntb - 1, 0);
+    const bool belt_ok = (cntb > 0) && (vz > F.vz_lo[b]);
     const int first = F.first[b];
     const int nb = F.first[b + 1] - first;
-    if (nb == 1) return first;                       // polar cap: every theta passes (0 via theta + 2 pi)
     float th = atan2f(vy, vx);
-    if (th < 0.f) th += 6.2831855f;
+    th += (th < 0.f) ? 6.2831855f : 0.f;
     float u = th - F.t0[b];
-    if (u < 0.f) u += 6.2831855f;
-    int k = (int)(u * F.k_scale[b]);
-    k = min(k, nb - 1);
-    const int z = first + k;
+    u += (u < 0.f) ? 6.2831855f : 0.f;
+    const int z = first + min((int)(u * F.k_scale[b]), nb - 1);
     const float sth = th + 6.2831855f;
-    if ((th > F.tmin[z] && th < F.tmax[z]) || (sth > F.tmin[z] && sth < F.tmax[z])) return z;
-    return -1;
+    const float tlo = F.tmin[z], thi = F.tmax[z];
+    const bool in = ((th > tlo) & (th < thi)) | ((sth > tlo) & (sth < thi));
+    // a polar cap (one zone in the belt) accepts every theta (theta = 0 passes through theta + 2 pi)
+    return (belt_ok && (in || nb == 1)) ? z : -1;
 }

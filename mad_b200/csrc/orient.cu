@@ -83,22 +83,43 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
     __syncthreads();
 
     // ---- step01 + first histogram (float32 angles against float64 bounds) ----
-    for (int i = tid; i < n_mask; i += blockDim.x) {
-        const char4 d = mask_off[i];
-        const long long idx = ((long long)(cx + s * d.x) * ny + (cy + s * d.y)) * nz + (cz + s * d.z);
-        float4 g = __ldg(grad + idx);
-        const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
-        if (m > 1e-5f) {
-            g.x = __fdiv_rn(g.x, m);
-            g.y = __fdiv_rn(g.y, m);
-            g.z = __fdiv_rn(g.z, m);
+    constexpr int GB = 4;                  // gathers issued per thread before the first one is consumed
+    for (int i0 = tid; i0 < n_mask; i0 += GB * blockDim.x) {
+        float4 gv[GB];
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+            const int i = i0 + u * blockDim.x;
+            gv[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n_mask) {
+                const char4 d = mask_off[i];
+                const long long idx = ((long long)(cx + s * d.x) * ny + (cy + s * d.y)) * nz + (cz + s * d.z);
+                gv[u] = __ldg(grad + idx);
+            }
         }
-        g.w = (m < 1e-5f) ? 0.f : 1.f;
-        pv[i] = g;
-        if (g.w != 0.f) {
-            const int zf = zone_fast(F, g.x, g.y, g.z);
-            if (zf >= 0) atomicAdd(&hist[zf], 1);
-            else vote_exact_f32(T, g.x, g.y, g.z, hist);
+        int zf[GB];
+        bool vote[GB];
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {                 // branch-free: the GB chains interleave
+            const int i = i0 + u * blockDim.x;
+            float4 g = gv[u];
+            const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
+            const float d = (m > 1e-5f) ? m : 1.f;     // normalise where magn > 1e-5 (mad/Orientator.py:160-163)
+            g.x = __fdiv_rn(g.x, d);
+            g.y = __fdiv_rn(g.y, d);
+            g.z = __fdiv_rn(g.z, d);
+            g.w = (m < 1e-5f) ? 0.f : 1.f;
+            gv[u] = g;
+            vote[u] = (i < n_mask) && (g.w != 0.f);
+            zf[u] = zone_fast(F, g.x, g.y, g.z);
+        }
+#pragma unroll
+        for (int u = 0; u < GB; ++u) {
+            const int i = i0 + u * blockDim.x;
+            if (i < n_mask) pv[i] = gv[u];
+            if (vote[u]) {
+                if (zf[u] >= 0) atomicAdd(&hist[zf[u]], 1);
+                else vote_exact_f32(T, gv[u].x, gv[u].y, gv[u].z, hist);
+            }
         }
     }
     __syncthreads();
@@ -136,14 +157,25 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
             float rf[9];
 #pragma unroll
             for (int q = 0; q < 9; ++q) rf[q] = (float)R[q];
-            for (int i = tid; i < n_mask; i += blockDim.x) {
-                const float4 g = pv[i];
-                if (g.w == 0.f) continue;
-                const int zf = zone_fast(F, fmaf(g.z, rf[2], fmaf(g.y, rf[1], g.x * rf[0])),
-                                         fmaf(g.z, rf[5], fmaf(g.y, rf[4], g.x * rf[3])),
-                                         fmaf(g.z, rf[8], fmaf(g.y, rf[7], g.x * rf[6])));
-                if (zf >= 0) atomicAdd(&hist[zf], 1);
-                else vote_exact_f64(T, R, g.x, g.y, g.z, hist);
+            for (int i0 = tid; i0 < n_mask; i0 += GB * blockDim.x) {
+                float4 gq[GB];
+                int zq[GB];
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    const int i = min(i0 + u * (int)blockDim.x, n_mask - 1);
+                    const float4 g = pv[i];
+                    gq[u] = g;
+                    zq[u] = zone_fast(F, fmaf(g.z, rf[2], fmaf(g.y, rf[1], g.x * rf[0])),
+                                      fmaf(g.z, rf[5], fmaf(g.y, rf[4], g.x * rf[3])),
+                                      fmaf(g.z, rf[8], fmaf(g.y, rf[7], g.x * rf[6])));
+                }
+#pragma unroll
+                for (int u = 0; u < GB; ++u) {
+                    if (i0 + u * (int)blockDim.x < n_mask && gq[u].w != 0.f) {
+                        if (zq[u] >= 0) atomicAdd(&hist[zq[u]], 1);
+                        else vote_exact_f64(T, R, gq[u].x, gq[u].y, gq[u].z, hist);
+                    }
+                }
             }
             __syncthreads();
             if (tid < T.n_zones) atomicMax(&s_hmax, hist[tid]);

@@ -418,6 +418,35 @@ def _match_threshold_onepass(hi, lo, cc, dev, st):
     return pair_hi[:p], pair_lo[:p], score[:p]
 
 
+class HostStage(object):
+    """Pinned host staging buffers for device -> host results, reused across calls: ``fetch`` starts
+    an asynchronous copy on the current stream and returns the CPU view, valid after ``sync()``."""
+
+    def __init__(self):
+        self.bufs = {}
+
+    def fetch(self, name, t):
+        n = t.numel() * t.element_size()
+        buf = self.bufs.get(name)
+        if buf is None or buf.numel() < n:
+            buf = torch.empty(max(n * 5 // 4, 256), dtype=torch.uint8).pin_memory()
+            self.bufs[name] = buf
+        view = buf[:n].view(t.dtype).view(t.shape)
+        if n:
+            view.copy_(t, non_blocking=True)
+        return view
+
+    def sync(self):
+        torch.cuda.current_stream().synchronize()
+
+
+def concat_sets(sets):
+    """One DescriptorSet holding the rows of several (e.g. all subunits of an assembly) + row offsets,
+    so that one matching launch serves them all; pairs come back with global hi rows."""
+    offs = np.cumsum([0] + [s.rows for s in sets]).astype(np.int64)
+    return DescriptorSet(torch.cat([s.dsc for s in sets], 0)), offs
+
+
 def match_topk(hi, lo, k=8, lo_index_base=0, impl=None):
     """Per hi row the k best lo rows by (score desc, index asc).  Device tensors (idx, score)."""
     hi, lo = _as_set(hi), _as_set(lo)

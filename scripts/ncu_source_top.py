@@ -2,10 +2,14 @@
 import csv
 import sys
 
-rows = list(csv.reader(open(sys.argv[1])))
+rows = [r for r in csv.reader(open(sys.argv[1]))]
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 40
 hdr = rows[1]
 ci = {h: i for i, h in enumerate(hdr)}
+which = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+starts = [i for i, r in enumerate(rows) if r and r[0] == "Kernel Name"] + [len(rows)]
+rows = rows[starts[which]:starts[which + 1]]
+print(rows[0][1][:100])
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 data = []
 for idx, r in enumerate(rows[2:]):

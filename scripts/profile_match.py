@@ -15,8 +15,10 @@ M = int(sys.argv[1]) if len(sys.argv) > 1 else 6784
 N = int(sys.argv[2]) if len(sys.argv) > 2 else 40320
 mode = sys.argv[3] if len(sys.argv) > 3 else "pairs"
 cc = float(sys.argv[4]) if len(sys.argv) > 4 else 0.6
-lo = synth.synthetic_descriptors(min(N, 8192), 7)
-lo = np.concatenate([lo] * ((N + len(lo) - 1) // len(lo)))[:N]
+base = synth.synthetic_descriptors(min(N, 8192), 7)
+rng = np.random.default_rng(11)
+reps = (N + len(base) - 1) // len(base)
+lo = np.concatenate([np.roll(base, int(rng.integers(0, 1024)), axis=1) if r else base for r in range(reps)])[:N]
 hi = synth.synthetic_descriptors(M, 8, noisy_copy_of=lo[:8192])
 dl, dh = P.DescriptorSet(lo), P.DescriptorSet(hi)
 for it in range(3):
