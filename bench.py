@@ -254,7 +254,9 @@ def main():
     def step_e2e():
         g = grid_pin.to(dev, non_blocking=True)
         sp, kp, ori, dsc = P.describe_struct(g, exact_f64=exact)
-        out = [stage.fetch("dsc", dsc), stage.fetch("kp", kp.table[:len(kp)]), stage.fetch("ori", ori.table[:len(ori)])]
+        # descriptor / keypoint / orientation tables go home on a side stream while matching runs
+        out = [stage.fetch("dsc", dsc, overlap=True), stage.fetch("kp", kp.table[:len(kp)], overlap=True),
+               stage.fetch("ori", ori.table[:len(ori)], overlap=True)]
         lo = P.DescriptorSet(dsc)
         ph, pl, sc = P.match_threshold(hi_all, lo, 0.6, impl=args.match_impl)
         out += [stage.fetch("ph", ph), stage.fetch("pl", pl), stage.fetch("sc", sc)]

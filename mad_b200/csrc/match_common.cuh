@@ -28,6 +28,41 @@ __host__ __device__ __forceinline__ void mad_topk_insert(double* bs, int* bi, in
     bi[q] = id;
 }
 
+// (s, id) ranks before (ps, pi) in the (score desc, index asc) order; empty slots (pi < 0) rank last.
+__host__ __device__ __forceinline__ bool mad_topk_before(double s, int id, double ps, int pi) {
+    return s > ps || (s == ps && (pi < 0 || id < pi));
+}
+
+// Register-resident list of exactly 8 entries (static indices only): new[q] = the old q-1 if the
+// candidate ranks before it, else the candidate if it ranks before the old q, else the old q.
+__device__ __forceinline__ void mad_top8_insert(double (&bs)[8], int (&bi)[8], double s, int id) {
+    bool c[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = mad_topk_before(s, id, bs[q], bi[q]);
+#pragma unroll
+    for (int q = 7; q >= 1; --q) {
+        bs[q] = c[q - 1] ? bs[q - 1] : (c[q] ? s : bs[q]);
+        bi[q] = c[q - 1] ? bi[q - 1] : (c[q] ? id : bi[q]);
+    }
+    bs[0] = c[0] ? s : bs[0];
+    bi[0] = c[0] ? id : bi[0];
+}
+
+// v[j] for a run-time j without spilling v to local memory: 5 levels of selects.
+__device__ __forceinline__ uint32_t mad_select32(const uint32_t (&v)[32], int j) {
+    uint32_t a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = (j & 1) ? v[2 * i + 1] : v[2 * i];
+    uint32_t b[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = (j & 2) ? a[2 * i + 1] : a[2 * i];
+    uint32_t c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = (j & 4) ? b[2 * i + 1] : b[2 * i];
+    const uint32_t d0 = (j & 8) ? c[1] : c[0], d1 = (j & 8) ? c[3] : c[2];
+    return (j & 16) ? d1 : d0;
+}
+
 // Both kernels cut the lo axis into S segments of `tiles_per_seg` 256-column tiles.
 #define MAD_MATCH_SEG_TILE 256
 

@@ -17,12 +17,14 @@
 //   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128 N=128 K=32, int32
 //                              accumulators in TMEM (4 x 128 columns, 4-deep)
 //   warp 2      TMEM allocator
-//   warps 4..7  epilogue     : tcgen05.ld (32 lanes x 32 columns), thread = one hi row
+//   warps 4..11 epilogue     : two groups of 4 warps alternating tiles; tcgen05.ld (32 lanes x 32
+//                              columns), thread = one hi row
 //        PAIRS mode: hits (row, col, dot) are staged per warp in shared memory and appended to a
 //                    global candidate list with one atomicAdd per flush; a radix sort by
 //                    (row, col) afterwards restores np.where's row-major order (match_finish).
 //        TOPK mode : per-row running top-k in the thread, one partial list per lo segment.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "match_common.cuh"
@@ -38,11 +40,12 @@ constexpr int STAGES = 5;
 constexpr int ACCS = 4;            // TMEM accumulator ring (4 x 128 columns)
 constexpr uint32_t KB_BYTES = BM * BKB;             // 16 KB: one k-block of 128 rows
 constexpr uint32_t A_BYTES = KBLOCKS * KB_BYTES;    // 128 KB resident hi tile
-constexpr int THREADS = 256;
+constexpr int EPI_WARPS = 8;       // two epilogue groups of 4 warps (one per TMEM lane quadrant), alternating tiles
+constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
-constexpr int STG = 192;           // staged candidates per epilogue warp
-constexpr size_t STG_BYTES = (size_t)4 * STG * (sizeof(unsigned long long) + sizeof(int));
-constexpr size_t RB_BYTES = (size_t)4 * 2 * BN * sizeof(float);   // per-warp, double-buffered 1/|lo| of a tile
+constexpr int STG = 96;            // staged candidates per epilogue warp
+constexpr size_t STG_BYTES = (size_t)EPI_WARPS * STG * (sizeof(unsigned long long) + sizeof(int));
+constexpr size_t RB_BYTES = (size_t)EPI_WARPS * 2 * BN * sizeof(float);   // per-warp, double-buffered 1/|lo| of a tile
 // dynamic smem: [1024 slack][A 128K][B ring 80K][staging 9K][rnorm 4K][barriers, tmem slot, counters 256]
 constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + RB_BYTES + 256;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one sm_100 CTA");
@@ -137,11 +140,11 @@ struct U8Args {
     unsigned long long* count;    // device counter (hits found, may exceed cap)
     // TOPK
     int k, lo_index_base;
-    int32_t* topk_idx;            // [S][M][k]
+    int32_t* topk_idx;            // [2 S][M][k]: one list per (segment, epilogue group)
     double* topk_score;
 };
 
-enum { MODE_PAIRS = 0, MODE_TOPK = 1 };
+enum { MODE_PAIRS = 0, MODE_TOPK = 1, MODE_TOP8 = 2, MODE_PAIRS_RELOAD = 3 };   // TOP8: k <= 8, list in registers
 
 template <int MODE>
 __global__ void __launch_bounds__(THREADS, 1)
@@ -152,9 +155,9 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     uint8_t* gen = smem_raw + (base - raw);
     const uint32_t b_ring = base + A_BYTES;
     constexpr uint32_t STG_OFF = A_BYTES + STAGES * KB_BYTES;
-    unsigned long long* stg_key = reinterpret_cast<unsigned long long*>(gen + STG_OFF);        // [4][STG]
-    int* stg_dot = reinterpret_cast<int*>(gen + STG_OFF + 4 * STG * sizeof(unsigned long long));   // [4][STG]
-    float* s_rb = reinterpret_cast<float*>(gen + STG_OFF + (uint32_t)STG_BYTES);                  // [4][2][BN]
+    unsigned long long* stg_key = reinterpret_cast<unsigned long long*>(gen + STG_OFF);        // [EPI_WARPS][STG]
+    int* stg_dot = reinterpret_cast<int*>(gen + STG_OFF + EPI_WARPS * STG * sizeof(unsigned long long));   // [EPI_WARPS][STG]
+    float* s_rb = reinterpret_cast<float*>(gen + STG_OFF + (uint32_t)STG_BYTES);                  // [EPI_WARPS][2][BN]
     constexpr uint32_t BAR_OFF = STG_OFF + (uint32_t)(STG_BYTES + RB_BYTES);
     const uint32_t bars = base + BAR_OFF;
     auto full_bar = [&](int s) { return bars + 8u * s; };
@@ -163,7 +166,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     auto tempty_bar = [&](int q) { return bars + 8u * (2 * STAGES + ACCS + q); };
     const uint32_t a_bar = bars + 8u * (2 * STAGES + 2 * ACCS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + BAR_OFF + 8 * (2 * STAGES + 2 * ACCS + 1));
-    int* s_cnt = reinterpret_cast<int*>(gen + BAR_OFF + 8 * (2 * STAGES + 2 * ACCS + 2));       // [4]
+    int* s_cnt = reinterpret_cast<int*>(gen + BAR_OFF + 8 * (2 * STAGES + 2 * ACCS + 2));       // [EPI_WARPS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int m0 = blockIdx.x * BM;
@@ -178,7 +181,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < 4) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < EPI_WARPS) s_cnt[threadIdx.x] = 0;
     if (warp == 2) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -237,6 +240,8 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     } else if (warp >= 4) {
         // ===================== epilogue: thread = one hi row =====================
         const int q = warp & 3;                                      // TMEM lane quadrant of this warp
+        const int ew = warp - 4;                                     // epilogue warp 0..7
+        const int grp = ew >> 2;                                     // group 0 takes even tiles of the sweep, group 1 odd
         const int row = m0 + q * 32 + lane;
         const bool row_ok = row < a.M;
         const int n2a_i = row_ok ? a.hi_n2[row] : 0;
@@ -244,62 +249,80 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         const float ra = n2a_i > 0 ? (float)(1.0 / sqrt(n2a)) : 0.f;
         // fp32 pre-filter: dot * rb > (cc - 4e-6) / ra   (|approx - exact| < 1e-6); never for zero rows
         const float thr_pairs = (row_ok && n2a_i > 0) ? ((float)a.cc - 4e-6f) / ra : INFINITY;
-        unsigned long long* my_key = stg_key + q * STG;
-        int* my_dot = stg_dot + q * STG;
-        volatile int* my_cnt = s_cnt + q;
-        double bs[MODE == MODE_TOPK ? MAD_TOPK_MAX : 1];
-        int bi[MODE == MODE_TOPK ? MAD_TOPK_MAX : 1];
-        float thr = -1.f;                                            // fp32 bound of the current k-th best
-        if (MODE == MODE_TOPK) {
+        unsigned long long* my_key = stg_key + ew * STG;
+        int* my_dot = stg_dot + ew * STG;
+        volatile int* my_cnt = s_cnt + ew;
+        constexpr bool kTop = (MODE == MODE_TOPK || MODE == MODE_TOP8);
+        constexpr bool kReload = (MODE == MODE_PAIRS_RELOAD);        // candidates re-read from TMEM, one column per step
+        constexpr int kList = (MODE == MODE_TOPK) ? MAD_TOPK_MAX : (MODE == MODE_TOP8 ? 8 : 1);
+        double bs[kList];
+        int bi[kList];
+        float thr = -1.f;                                            // fp32 bound of the current worst list entry
+        if (kTop) {
 #pragma unroll
-            for (int i = 0; i < (MODE == MODE_TOPK ? MAD_TOPK_MAX : 1); ++i) { bs[i] = -INFINITY; bi[i] = -1; }
+            for (int i = 0; i < kList; ++i) { bs[i] = -INFINITY; bi[i] = -1; }
         }
+        const int k_last = (MODE == MODE_TOP8) ? 7 : a.k - 1;        // TOP8 keeps 8 entries whatever k <= 8 is
         // Candidates that pass the fp32 pre-filter are only STAGED here (two shared-memory stores);
         // the float64 test runs at flush time with the lanes working on 32 candidates in parallel,
         // so its latency (L2 load of the lo norm, DSQRT, DDIV) is not serialised per hit.
-        auto exact_and_emit = [&](unsigned long long key, int dot, bool have) {
-            bool ok = false;
-            if (have) {
-                const int r = (int)(key >> 32), c = (int)(key & 0xFFFFFFFFull);
-                if (r < a.M && c < a.N) {
-                    const double s = mad_score(dot, (double)__ldg(a.hi_n2 + r), (double)__ldg(a.lo_n2 + c));
-                    ok = s > a.cc;
-                }
-            }
-            const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-            if (m) {
-                unsigned long long gb = 0;
-                if (lane == 0) gb = atomicAdd(a.count, (unsigned long long)__popc(m));
-                gb = __shfl_sync(0xFFFFFFFFu, gb, 0) + __popc(m & ((1u << lane) - 1u));
-                if (ok && gb < a.cap) { a.cand_key[gb] = key; a.cand_dot[gb] = dot; }
-            }
-        };
         auto flush = [&]() {
+            // Pass 1: exact float64 test of 32 staged candidates per round, survivors compacted in
+            // place (a survivor's slot is never above the slot it was read from).  Pass 2: ONE global
+            // atomicAdd reserves the output range, then a coalesced copy.
             __syncwarp();
             const int n = min((int)*my_cnt, STG);
+            int total = 0;
             for (int i0 = 0; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
-                const bool have = i < n;
-                exact_and_emit(have ? my_key[i] : 0ull, have ? my_dot[i] : 0, have);
+                unsigned long long key = 0ull;
+                int dot = 0;
+                bool ok = false;
+                if (i < n) {
+                    key = my_key[i];
+                    dot = my_dot[i];
+                    const int r = (int)(key >> 32), c = (int)(key & 0xFFFFFFFFull);
+                    if (r < a.M && c < a.N) {
+                        const double s = mad_score(dot, (double)__ldg(a.hi_n2 + r), (double)__ldg(a.lo_n2 + c));
+                        ok = s > a.cc;
+                    }
+                }
+                const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
+                __syncwarp();
+                if (ok) {
+                    const int p = total + __popc(m & ((1u << lane) - 1u));
+                    my_key[p] = key;
+                    my_dot[p] = dot;
+                }
+                total += __popc(m);
+                __syncwarp();
+            }
+            if (total > 0) {
+                unsigned long long gb = 0;
+                if (lane == 0) gb = atomicAdd(a.count, (unsigned long long)total);
+                gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
+                for (int i = lane; i < total; i += 32)
+                    if (gb + i < a.cap) { a.cand_key[gb + i] = my_key[i]; a.cand_dot[gb + i] = my_dot[i]; }
             }
             __syncwarp();
             if (lane == 0) *my_cnt = 0;
             __syncwarp();
         };
-        float* my_rb = s_rb + q * 2 * BN;
+        float* my_rb = s_rb + ew * 2 * BN;
         auto stage_rb = [&](int t, int buf) {                        // 128 floats of this tile: lane -> one float4
             const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.lo_rnorm + (long long)t * BN) + lane);
             reinterpret_cast<float4*>(my_rb + buf * BN)[lane] = r4;
         };
-        int it = 0;
-        if (t_begin < t_end) stage_rb(t_begin, 0);
-        for (int t = t_begin; t < t_end; ++t, ++it) {
+        int it = grp;                                                // position of the tile in this CTA's sweep
+        int par = 0;                                                 // which rnorm buffer holds the current tile
+        if (t_begin + grp < t_end) stage_rb(t_begin + grp, 0);
+        for (int t = t_begin + grp; t < t_end; t += 2, it += 2, par ^= 1) {
             const int acc = it % ACCS;
             const uint32_t acc_phase = (uint32_t)(it / ACCS) & 1u;
             const int n0 = t * BN;
-            if (t + 1 < t_end) stage_rb(t + 1, (it + 1) & 1);        // next tile's norms: latency hidden by this tile
+            if (t + 2 < t_end) stage_rb(t + 2, par ^ 1);             // this group's next tile: latency hidden by this tile
             __syncwarp();
-            const float* rbt = my_rb + (it & 1) * BN;
+            const float* rbt = my_rb + par * BN;
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
@@ -317,30 +340,42 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 // Branch-free pre-filter over the 32 columns (the epilogue must stay small: an unrolled
                 // branchy body overflowed the instruction cache and made the epilogue the bottleneck);
                 // the rare candidates are then fetched again from TMEM one column at a time.
-                const float lim = (MODE == MODE_TOPK) ? (row_ok && ra > 0.f ? thr / ra : INFINITY) : thr_pairs;
+                const float lim = kTop ? (row_ok && ra > 0.f ? thr / ra : INFINITY) : thr_pairs;
                 unsigned mask = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
                     const float sc = (float)(int)v[j] * rb[j];
-                    const bool pass = (MODE == MODE_TOPK) ? (sc >= lim) : (sc > lim);
+                    const bool pass = kTop ? (sc >= lim) : (sc > lim);
                     mask |= (pass ? 1u : 0u) << j;
                 }
                 // zero row: every score is 0 and ties go to the lowest index -- only the first k columns matter
-                if (MODE == MODE_TOPK && row_ok && ra == 0.f) mask = (bi[a.k - 1] < 0) ? 0xFFFFFFFFu : 0u;
-                unsigned any = __reduce_or_sync(0xFFFFFFFFu, mask);
+                if (kTop && row_ok && ra == 0.f) mask = (bi[MODE == MODE_TOP8 ? 7 : k_last] < 0) ? 0xFFFFFFFFu : 0u;
+                // each lane walks its own (rare) candidates; the value comes out of the registers
+                // through a select tree, so lanes with candidates in different columns run together
+                unsigned any = kReload ? __reduce_or_sync(0xFFFFFFFFu, mask) : mask;
                 while (any) {
                     const int j = __ffs(any) - 1;
                     any &= any - 1;
-                    const int dot = (int)tmem_ld1(taddr + (uint32_t)(c0 + j));
-                    tmem_ld_wait();
-                    if (!((mask >> j) & 1u)) continue;
+                    int dot;
+                    if (kReload) {
+                        dot = (int)tmem_ld1(taddr + (uint32_t)(c0 + j));
+                        tmem_ld_wait();
+                        if (!((mask >> j) & 1u)) continue;
+                    } else {
+                        dot = (int)mad_select32(v, j);
+                    }
                     const int col = n0 + c0 + j;
-                    if (MODE == MODE_TOPK) {
+                    if (kTop) {
                         if (col < a.N) {
                             const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
-                            mad_topk_insert(bs, bi, a.k, s, a.lo_index_base + col);
-                            const double kth = bs[a.k - 1];
-                            thr = (bi[a.k - 1] < 0) ? -1.f : (float)kth - 4e-6f;
+                            if (MODE == MODE_TOP8) {
+                                mad_top8_insert(reinterpret_cast<double(&)[8]>(bs), reinterpret_cast<int(&)[8]>(bi), s,
+                                                a.lo_index_base + col);
+                                thr = (bi[kList - 1] < 0) ? -1.f : (float)bs[kList - 1] - 4e-6f;
+                            } else {
+                                mad_topk_insert(bs, bi, a.k, s, a.lo_index_base + col);
+                                thr = (bi[k_last] < 0) ? -1.f : (float)bs[k_last] - 4e-6f;
+                            }
                         }
                     } else {                                         // rnorm is 0 beyond N: padded columns never pass (cc > 0)
                         const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
@@ -357,7 +392,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                         }
                     }
                 }
-                if (MODE == MODE_PAIRS) {
+                if (!kTop) {
                     __syncwarp();
                     if (*my_cnt >= STG / 2) flush();
                 }
@@ -366,10 +401,17 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(acc));             // 4 arrivals free the accumulator
         }
-        if (MODE == MODE_PAIRS) flush();
-        if (MODE == MODE_TOPK && row_ok) {
-            const long long o = ((long long)seg * a.M + row) * a.k;
-            for (int i = 0; i < a.k; ++i) { a.topk_idx[o + i] = bi[i]; a.topk_score[o + i] = bs[i]; }
+        if (!kTop) flush();
+        if (kTop && row_ok) {
+            // one partial list per (segment, epilogue group): the host merges 2 S lists
+            const long long o = ((long long)(seg * 2 + grp) * a.M + row) * a.k;
+            if (MODE == MODE_TOP8) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < a.k) { a.topk_idx[o + i] = bi[i]; a.topk_score[o + i] = bs[i]; }
+            } else {
+                for (int i = 0; i < a.k; ++i) { a.topk_idx[o + i] = bi[i]; a.topk_score[o + i] = bs[i]; }
+            }
         }
     }
     tc_fence_before();
@@ -468,10 +510,16 @@ int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, i
     a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN), a.S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = cc;
     a.cand_key = cand_key; a.cand_dot = cand_dot; a.cap = cap; a.count = count;
-    MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     dim3 grid((unsigned)mad_ceil_div(M, BM), (unsigned)a.S);
+    static const bool use_select = getenv("MAD_PAIRS_SELECT") != nullptr;    // experiment switch (measurement only)
     MAD_PROF("match_u8_pairs_kernel", st);
-    match_u8_kernel<MODE_PAIRS><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    if (use_select) {
+        MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        match_u8_kernel<MODE_PAIRS><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    } else {
+        MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_PAIRS_RELOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        match_u8_kernel<MODE_PAIRS_RELOAD><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    }
     MAD_LAUNCH_OK();
     return MAD_OK;
 }
@@ -487,10 +535,15 @@ int mad_match_u8_topk(const void* hi_u8, int M, int M_pad, const void* lo_u8, in
     a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN), S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = 0.0;
     a.k = k; a.lo_index_base = lo_index_base; a.topk_idx = topk_idx; a.topk_score = topk_score;
-    MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     dim3 grid((unsigned)mad_ceil_div(M, BM), (unsigned)S);
     MAD_PROF("match_u8_topk_kernel", st);
-    match_u8_kernel<MODE_TOPK><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    if (k <= 8) {
+        MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_TOP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        match_u8_kernel<MODE_TOP8><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    } else {
+        MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        match_u8_kernel<MODE_TOPK><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    }
     MAD_LAUNCH_OK();
     return MAD_OK;
 }

@@ -103,10 +103,13 @@ struct GaussStream {
     }
 };
 
+// ring slot of sample i: i mod 48 (48 = chunk + look-ahead; exact for i < 130 000)
+__device__ __forceinline__ int ring_slot(int i) { return i - 48 * ((i * 43691) >> 21); }
+
 template <int GR, class IO>
 __device__ __forceinline__ void spline_line(IO& io, const int n, const SplineParams& prm,
                                             double* ring, const int rs) {
-    constexpr int C = 32, L = 32, RM = 63;
+    constexpr int C = 16, L = 32;
     const int last = n - 3;
     const double M1 = (io.y(0) - 2.0 * io.y(1)) + io.y(2);
     const double Mn2 = (io.y(n - 3) - 2.0 * io.y(n - 2)) + io.y(n - 1);
@@ -132,7 +135,7 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
                     if (fwd == 2) r -= M1;
                     if (fwd == last) r -= Mn2;
                     const double x = (r - xprev) * prm.cprime[fwd < 39 ? fwd : 39];
-                    ring[(fwd & RM) * rs] = x;
+                    ring[ring_slot(fwd) * rs] = x;
                     xprev = x;
                     ya = yb;
                     yb = yc;
@@ -144,15 +147,15 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
         double Me = 0.0;
         if (lo <= last) {
             int j = top;
-            double M = ring[(j & RM) * rs];
+            double M = ring[ring_slot(j) * rs];
             for (;;) {
                 if (j == last) Mn3v = M;
                 if (j == 2) M2v = M;
-                if (j < e) ring[(j & RM) * rs] = M;
+                if (j < e) ring[ring_slot(j) * rs] = M;
                 else if (j == e) Me = M;
                 if (j == lo) break;
                 --j;
-                M = fma(-prm.cprime[j < 39 ? j : 39], M, ring[(j & RM) * rs]);
+                M = fma(-prm.cprime[j < 39 ? j : 39], M, ring[ring_slot(j) * rs]);
             }
         }
         auto Mval = [&](int i) -> double {
@@ -161,7 +164,7 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
             if (i == n - 2) return Mn2;
             if (i == n - 1) return 2.0 * Mn2 - Mn3v;
             if (i == e) return Me;
-            return ring[(i & RM) * rs];
+            return ring[ring_slot(i) * rs];
         };
         double Mi = Mval(s);
         double yi = io.y(s);
@@ -205,7 +208,7 @@ template <typename TIn, typename TOut, int GR>
 __global__ void __launch_bounds__(128)
 spline_up_strided_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int n, long long inner,
                          long long total_lines, SplineParams prm) {
-    extern __shared__ double ring_s[];  // [64][blockDim.x]
+    extern __shared__ double ring_s[];  // [48][blockDim.x]
     const long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (g >= total_lines) return;
     const long long o = g / inner, j = g % inner;
@@ -218,16 +221,16 @@ spline_up_strided_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int
 
 // Lines along the contiguous axis: one warp owns 32 consecutive lines; the input lines are staged
 // in shared memory with coalesced loads, outputs are staged per chunk and flushed row by row.
-constexpr int kZStage = 81;  // >= 2*32 outputs per chunk (+ GR at the end); odd row stride (in doubles) avoids bank conflicts
+constexpr int kZStage = 49;  // >= 2*16 outputs per chunk (+ 2*GR at the end); odd row stride (in doubles) avoids bank conflicts
 struct ZLineIO {
-    const float* yline;   // this lane's line in shared memory
+    const float* yline;   // this lane's line in global memory (read through L1: a sector serves 8 steps)
     double* ostage;       // [32][kZStage]
     double* out;          // global, first line of this warp
     long long N;          // output line length (2n-1)
     int lines_valid;      // lines of this warp that exist
     int lane;
     int kbase, cnt;
-    __device__ __forceinline__ double y(int i) const { return (double)yline[i]; }
+    __device__ __forceinline__ double y(int i) const { return (double)__ldg(yline + i); }
     __device__ __forceinline__ void put(int k, double v) {
         ostage[lane * kZStage + (k - kbase)] = v;
         ++cnt;
@@ -242,24 +245,23 @@ struct ZLineIO {
     }
 };
 
+// Lines along the contiguous axis: a warp owns 32 consecutive lines (lane = line).  Inputs are read
+// straight from global memory (each lane walks its own line; the 32-byte sectors are reused from
+// L1 for 8 steps), outputs are staged per chunk in shared memory and flushed row by row (coalesced).
+// 4 warps per CTA, each with its own ring and output stage: no block-level barrier.
 template <int GR>
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(128)
 spline_up_z_kernel(const float* __restrict__ in, double* __restrict__ out, int n, long long total_lines,
                    int npad, SplineParams prm) {
     extern __shared__ double zs[];
-    double* ring = zs;                      // [64][32]
-    double* ostage = zs + 64 * 32;          // [32][kZStage]
-    float* ylines = reinterpret_cast<float*>(ostage + 32 * kZStage);  // [32][npad]
-    const int lane = threadIdx.x;
-    const long long l0 = (long long)blockIdx.x * 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double* ring = zs + (size_t)warp * (48 * 32 + 32 * kZStage);   // [48][32]
+    double* ostage = ring + 48 * 32;                                // [32][kZStage]
+    const long long l0 = ((long long)blockIdx.x * 4 + warp) * 32;
+    if (l0 >= total_lines) return;
     const int valid = (int)min((long long)32, total_lines - l0);
-    for (int r = 0; r < 32; ++r) {
-        const long long line = l0 + min(r, valid - 1);   // tail lanes recompute the last line
-        for (int t = lane; t < n; t += 32) ylines[r * npad + t] = __ldg(in + line * n + t);
-    }
-    __syncwarp();
     ZLineIO io;
-    io.yline = ylines + lane * npad;
+    io.yline = in + (l0 + min(lane, valid - 1)) * n;               // tail lanes recompute the last line
     io.ostage = ostage;
     io.out = out + l0 * (long long)(2 * n - 1);
     io.N = 2 * n - 1;
@@ -267,6 +269,7 @@ spline_up_z_kernel(const float* __restrict__ in, double* __restrict__ out, int n
     io.lane = lane;
     io.kbase = 0;
     io.cnt = 0;
+    (void)npad;
     spline_line<GR>(io, n, prm, ring + lane, 32);
 }
 
@@ -291,17 +294,13 @@ static int upsample_launch(const float* base, int bx, int by, int bz, const Spli
     {
         const long long lines = (long long)bx * by;
         const int npad = bz | 1;
-        const size_t smem = (64 * 32 + 32 * kZStage) * sizeof(double) + (size_t)32 * npad * sizeof(float);
-        if (smem > 200 * 1024) {
-            mad_set_error("mad_upsample_presmooth: z extent %d too long for the shared-memory line stage", bz);
-            return MAD_ERR_ARG;
-        }
+        const size_t smem = (size_t)4 * (48 * 32 + 32 * kZStage) * sizeof(double);
         MAD_CUDA(cudaFuncSetAttribute(spline_up_z_kernel<GR>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         MAD_PROF("spline_up_z_kernel", st);
-        spline_up_z_kernel<GR><<<(unsigned)mad_ceil_div(lines, 32), 32, smem, st>>>(base, wsA, bz, lines, npad, prm);
+        spline_up_z_kernel<GR><<<(unsigned)mad_ceil_div(lines, 128), 128, smem, st>>>(base, wsA, bz, lines, npad, prm);
         MAD_LAUNCH_OK();
     }
-    const size_t ring_smem = 64 * 128 * sizeof(double);
+    const size_t ring_smem = 48 * 128 * sizeof(double);
     // pass X: f64 [bx][by][Z] -> f64 [2bx-1][by][Z],  Z = 2bz-1
     {
         const long long inner = (long long)by * (2 * bz - 1);
@@ -496,7 +495,7 @@ log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__
 // type, one input array after the other; results are staged in shared memory and written as
 // whole rows (coalesced).
 template <int R, typename ACC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(384)
 log_pass_z_kernel(const float* __restrict__ P01, const float* __restrict__ Rr, const float* __restrict__ S,
                   float* __restrict__ log_out, float* __restrict__ gauss_out, int nz, long long n_rows,
                   int rows_per_cta, int rs_in, int rs_out, long long n_batches, float scale, ConvW w) {
@@ -514,7 +513,7 @@ log_pass_z_kernel(const float* __restrict__ P01, const float* __restrict__ Rr, c
             float* d0 = zsm + buf * in_buf;
             for (int r = 0; r < rows; ++r) {
                 const long long gb = (row0 + r) * nz;
-                for (int t = tid; t < halo_len; t += 128) {
+                for (int t = tid; t < halo_len; t += blockDim.x) {
                     const long long src = gb + mad_reflect(t - R, nz);
                     float* d = d0 + r * rs_in + t;
                     cp_async4(d, P01 + src);
@@ -624,16 +623,17 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
         const int rs_in = (n_chunks * 8 + 2 * R + 3) / 4 * 4;
         const int rs_out = (nz + 3) / 4 * 4;
         const size_t row_bytes = (size_t)(2 * 3 * rs_in + 2 * rs_out) * sizeof(float);   // double-buffered inputs + outputs
-        // rows per batch: the value (within ~72 KB of shared memory, 3 CTAs per SM) that leaves the
-        // fewest idle threads in the last pass over rows x chunks
+        // rows per batch and threads per CTA: the pair (within ~72 KB of shared memory, 3 CTAs per
+        // SM) that leaves the fewest idle threads over the rows x chunks work items of a batch
         const int max_rows = (int)std::max<size_t>(1, std::min<size_t>(32, (72 * 1024) / row_bytes));
-        int rows = 1;
+        int rows = 1, threads = 128;
         double best_eff = -1.0;
-        for (int r = 1; r <= max_rows; ++r) {
-            const long long work = (long long)r * n_chunks;
-            const double eff = (double)work / (double)(mad_ceil_div(work, 128) * 128);
-            if (eff > best_eff + 1e-9 || (eff > best_eff - 1e-9 && r > rows)) { best_eff = std::max(best_eff, eff); rows = r; }
-        }
+        for (int r = 1; r <= max_rows; ++r)
+            for (int th = 128; th <= 128; th += 32) {    // wider CTAs measured slower (fewer resident CTAs to overlap the phases)
+                const long long work = (long long)r * n_chunks;
+                const double eff = (double)work / (double)(mad_ceil_div(work, th) * th);
+                if (eff > best_eff + 1e-9) { best_eff = eff; rows = r; threads = th; }
+            }
         const size_t smem = rows * row_bytes;
         if (smem > 200 * 1024) {
             mad_set_error("mad_log_gauss: z extent %d too long for the shared-memory row stage", nz);
@@ -644,7 +644,7 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
         const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(216 * 1024) / std::max<size_t>(smem, 1)));
         const unsigned grid_z = (unsigned)std::min<long long>(n_batches, (long long)sms * ctas_per_sm);
         MAD_PROF("log_pass_z_kernel", st);
-        log_pass_z_kernel<R, ACC><<<grid_z, 128, smem, st>>>(P01, Rr, S, log_out, gauss_out, nz, n_rows, rows, rs_in, rs_out, n_batches, scale, w);
+        log_pass_z_kernel<R, ACC><<<grid_z, threads, smem, st>>>(P01, Rr, S, log_out, gauss_out, nz, n_rows, rows, rs_in, rs_out, n_batches, scale, w);
         MAD_LAUNCH_OK();
     }
     return MAD_OK;

@@ -424,20 +424,37 @@ class HostStage(object):
 
     def __init__(self):
         self.bufs = {}
+        self.copy_stream = None
+        self.keep = []
 
-    def fetch(self, name, t):
+    def fetch(self, name, t, overlap=False):
+        """overlap=True: the copy runs on a side stream (after everything queued so far on the
+        current stream), so later kernels on the current stream are not held up by the PCIe copy."""
         n = t.numel() * t.element_size()
         buf = self.bufs.get(name)
         if buf is None or buf.numel() < n:
             buf = torch.empty(max(n * 5 // 4, 256), dtype=torch.uint8).pin_memory()
             self.bufs[name] = buf
         view = buf[:n].view(t.dtype).view(t.shape)
-        if n:
+        if not n:
+            return view
+        if overlap:
+            if self.copy_stream is None:
+                self.copy_stream = torch.cuda.Stream()
+            self.copy_stream.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self.copy_stream):
+                view.copy_(t, non_blocking=True)
+            t.record_stream(self.copy_stream)
+            self.keep.append(t)
+        else:
             view.copy_(t, non_blocking=True)
         return view
 
     def sync(self):
         torch.cuda.current_stream().synchronize()
+        if self.copy_stream is not None:
+            self.copy_stream.synchronize()
+        self.keep = []
 
 
 def concat_sets(sets):

@@ -365,3 +365,55 @@ def test_entries_above_255_use_the_fp16_kernel(P):
         assert torch.equal(x, y)
     with pytest.raises(MadError):
         P.match_threshold(hi, lo, 0.5, impl=0)
+
+
+def test_stacked_hi_sets_equal_separate_matches(P):
+    """concat_sets: one launch over the stacked hi sets returns exactly the per-set pair lists
+    (global hi row = offset + local row), in the same order."""
+    import synth
+    lo = synth.synthetic_descriptors(700, 41)
+    his = [synth.synthetic_descriptors(m, 42 + i, noisy_copy_of=lo) for i, m in enumerate((130, 1, 257))]
+    sets = [P.DescriptorSet(h) for h in his]
+    allset, offs = P.concat_sets(sets)
+    dl = P.DescriptorSet(lo)
+    ph, pl, sc = [t.cpu().numpy() for t in P.match_threshold(allset, dl, 0.55)]
+    for i, s in enumerate(sets):
+        a = [t.cpu().numpy() for t in P.match_threshold(s, dl, 0.55)]
+        sel = (ph >= offs[i]) & (ph < offs[i + 1])
+        assert np.array_equal(ph[sel] - offs[i], a[0]) and np.array_equal(pl[sel], a[1]) and np.array_equal(sc[sel], a[2])
+
+
+def test_host_stage_roundtrip(P):
+    st = P.HostStage()
+    x = torch.arange(1000, dtype=torch.int32, device="cuda").reshape(100, 10)
+    a = st.fetch("x", x)
+    b = st.fetch("y", x.double() * 0.5, overlap=True)
+    st.sync()
+    assert np.array_equal(a.numpy(), x.cpu().numpy()) and np.array_equal(b.numpy(), x.cpu().numpy() * 0.5)
+
+
+def test_c3_size_scale_space_linearity(P):
+    """BASELINE config 3 size (512^3 -> 530^3 + 1059^3 grids, ~50 GB of device arrays): the stencil
+    chain runs at that size and is exactly linear under power-of-two scaling; detection on the
+    halved map equals detection on the original with the threshold doubled."""
+    g = torch.Generator(device="cuda").manual_seed(3)
+    n = 512
+    coarse = torch.rand((1, 1, 20, 20, 20), device="cuda", generator=g)
+    grid = torch.nn.functional.interpolate(coarse, size=(n, n, n), mode="trilinear", align_corners=True)[0, 0]
+    grid = (grid - 0.45).clamp_(min=0).contiguous()
+    grid /= grid.max()
+    a = P.build_space(grid, keep_gauss=False)
+    ka = P.detect(a).host().copy()
+    la = [t.clone() for t in a.logs]
+    ga = a.grad4[1][::7, ::5, ::3].clone()
+    del a
+    torch.cuda.empty_cache()
+    b = P.build_space(grid * 0.5, keep_gauss=False)
+    kb = P.detect(b).host()
+    for o in range(2):
+        big = la[o].abs() > 1e-30
+        assert torch.equal(la[o][big] * 0.5, b.logs[o][big])
+    assert torch.equal(ga * 0.5, b.grad4[1][::7, ::5, ::3])
+    keep = ka["val"] * np.float32(0.5) > np.float32(0.05)
+    assert len(ka) > 100 and keep.sum() == len(kb)
+    assert np.array_equal(ka["vox"][keep], kb["vox"]) and np.array_equal(ka["off"][keep], kb["off"])
