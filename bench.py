@@ -199,7 +199,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=["c2", "c5"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--match-impl", type=int, default=None, help="default: product (uint8 tcgen05 one-pass); 1 = SIMT check, 2 = fp16 tcgen05")
     ap.add_argument("--exact", type=int, default=1, help="1 = float64 line accumulation (bit-exact with SciPy)")
@@ -210,6 +210,9 @@ def main():
     if args.workload == "c5":
         import bench_match
         return bench_match.main(args)
+    if args.workload == "c4":
+        import bench_batch
+        return bench_batch.main(args)
 
     import torch
     import torch.distributed as dist

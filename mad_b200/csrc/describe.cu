@@ -14,11 +14,10 @@ namespace {
 
 struct OctDims { int n[2][3]; };
 
-__device__ __forceinline__ int nearest_idx(double p, int n) {
-    int i = (int)floor(p);
-    i = max(0, min(i, n - 2));
-    return (p - (double)i <= 0.5) ? i : i + 1;     // scipy _rgi: where(norm_dist <= .5, i, i + 1)
-}
+// scipy _rgi nearest rule: i = clip(floor(p), 0, n-2); idx = (p - i <= .5) ? i : i + 1 -- a half rounds
+// DOWN.  For p in [0, n-1] (guaranteed by the bounds vote) this is exactly ceil(p - 0.5): p - 0.5 is
+// exact for p >= 0.5 and stays in [-0.5, 0) below.
+__device__ __forceinline__ int nearest_idx(double p) { return __double2int_ru(p - 0.5); }
 
 // Exact (reference-arithmetic) classification of one direction: float64 rotation, atan2, acos and
 // the strict-inequality zone test.  Kept out of line: it runs for ~0.1 % of the samples and must
@@ -115,23 +114,22 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
                 const double px = ((lx * Ri[0] + ay0) + az0) + cx;
                 const double py = ((lx * Ri[3] + ay1) + az1) + cy;
                 const double pz = ((lx * Ri[6] + ay2) + az2) + cz;
-                const int ix = nearest_idx(px, nx), iy = nearest_idx(py, ny), iz = nearest_idx(pz, nz);
+                const int ix = nearest_idx(px), iy = nearest_idx(py), iz = nearest_idx(pz);
                 gv[u] = __ldg(grad + ((long long)ix * ny + iy) * nz + iz);
             }
-            float vx[GB], vy[GB], vz[GB], gx[GB], gy[GB], gz[GB];
+            float vx[GB], vy[GB], vz[GB];
             bool valid[GB];
 #pragma unroll
             for (int u = 0; u < GB; ++u) {
                 const float4 g = gv[u];
-                const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
-                valid[u] = (i0 + u < side) && !(m < 1e-5f);     // m < 1e-5: zone -1, never counted (:190)
-                const float d = (m > 1e-12f) ? m : 1.f;         // normalise where m > 1e-12 (:160-163)
-                gx[u] = __fdiv_rn(g.x, d);
-                gy[u] = __fdiv_rn(g.y, d);
-                gz[u] = __fdiv_rn(g.z, d);
-                vx[u] = (gx[u] * Rmf[0] + gy[u] * Rmf[1]) + gz[u] * Rmf[2];
-                vy[u] = (gx[u] * Rmf[3] + gy[u] * Rmf[4]) + gz[u] * Rmf[5];
-                vz[u] = (gx[u] * Rmf[6] + gy[u] * Rmf[7]) + gz[u] * Rmf[8];
+                // squared magnitude with the reference's float32 rounding; m < 1e-5 (zone -1, never counted,
+                // :190) is decided exactly on m2; the fast path normalises with rsqrt (margin-covered)
+                const float m2 = __fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z));
+                valid[u] = (i0 + u < side) && !(m2 < MAD_M2_LT);
+                const float rinv = rsqrtf(fmaxf(m2, 1e-30f));
+                vx[u] = ((g.x * Rmf[0] + g.y * Rmf[1]) + g.z * Rmf[2]) * rinv;
+                vy[u] = ((g.x * Rmf[3] + g.y * Rmf[4]) + g.z * Rmf[5]) * rinv;
+                vz[u] = ((g.x * Rmf[6] + g.y * Rmf[7]) + g.z * Rmf[8]) * rinv;
             }
             int zone[GB];
 #pragma unroll
@@ -139,8 +137,13 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
 #pragma unroll
             for (int u = 0; u < GB; ++u) {
                 if (valid[u]) {
-                    // directions within 2e-5 rad of a zone edge take the exact float64 path
-                    if (zone[u] < 0) zone[u] = zone_exact_dsc(T, rf_table + tab, gx[u], gy[u], gz[u]);
+                    // directions within 2e-5 rad of a zone edge take the exact path: float32 sqrt and
+                    // divisions as NumPy does them (m > 1e-12 holds since m >= 1e-5), float64 rotation
+                    if (zone[u] < 0) {
+                        const float4 g = gv[u];
+                        const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
+                        zone[u] = zone_exact_dsc(T, rf_table + tab, __fdiv_rn(g.x, m), __fdiv_rn(g.y, m), __fdiv_rn(g.z, m));
+                    }
                     const int i = i0 + u;
                     const int bx = (i >= c1) + (i >= c2) + (i >= c3);
                     atomicAdd(&cnt[bin_jk + 4 * bx * T.n_zones + zone[u]], 1);

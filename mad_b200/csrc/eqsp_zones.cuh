@@ -60,6 +60,32 @@ __device__ __forceinline__ int zones_of(const ZoneTab& T, double th, double sth,
 #define MAD_ZONE_MAX 128
 #define MAD_BELT_MAX 32
 
+// Exact squared-magnitude forms of the reference's float32 cut-offs on m = sqrt(m2) (sqrt is
+// monotone and correctly rounded):  m < 1e-5f  <=>  m2 < MAD_M2_LT;   m > 1e-5f  <=>  m2 >= MAD_M2_GT.
+#define MAD_M2_LT __uint_as_float(0x2edbe6fdu)
+#define MAD_M2_GT __uint_as_float(0x2edbe700u)
+
+// atan2 mapped to [0, 2 pi), |error| < 1e-6 rad: degree-13 odd minimax polynomial on min/max (fitted
+// and checked over 2e6 float32 arguments: 3.2e-7) + fast division; ~20 instructions instead of ~45.
+__device__ __forceinline__ float mad_atan2_2pi(float y, float x) {
+    const float ax = fabsf(x), ay = fabsf(y);
+    const float mx = fmaxf(ax, ay), mn = fminf(ax, ay);
+    const float a = (mx > 0.f) ? __fdividef(mn, mx) : 0.f;
+    const float s = a * a;
+    float p = 0.006811789236962795f;
+    p = fmaf(p, s, -0.0336042121052742f);
+    p = fmaf(p, s, 0.07962366938591003f);
+    p = fmaf(p, s, -0.1323334276676178f);
+    p = fmaf(p, s, 0.19807815551757812f);
+    p = fmaf(p, s, -0.3331736922264099f);
+    p = fmaf(p, s, 0.9999961256980896f);
+    p *= a;
+    p = (ay > ax) ? 1.5707964f - p : p;
+    p = (x < 0.f) ? 3.1415927f - p : p;
+    p = (y < 0.f) ? 6.2831855f - p : p;
+    return p;
+}
+
 struct ZoneFast {                    // per-CTA copy in shared memory (zone_fast_init)
     float tmin[MAD_ZONE_MAX];        // theta bounds shrunk by eps
     float tmax[MAD_ZONE_MAX];
@@ -101,8 +127,7 @@ __device__ __forceinline__ int zone_fast(const ZoneFast& F, float vx, float vy, 
     const bool belt_ok = (cntb > 0) && (vz > F.vz_lo[b]);
     const int first = F.first[b];
     const int nb = F.first[b + 1] - first;
-    float th = atan2f(vy, vx);
-    th += (th < 0.f) ? 6.2831855f : 0.f;
+    const float th = mad_atan2_2pi(vy, vx);
     float u = th - F.t0[b];
     u += (u < 0.f) ? 6.2831855f : 0.f;
     const int z = first + min((int)(u * F.k_scale[b]), nb - 1);

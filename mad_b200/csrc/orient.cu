@@ -21,9 +21,20 @@ __device__ __forceinline__ int norm50(int h, int hmax) {
 }
 
 // Exact (reference-arithmetic) votes of one direction; out of line, they run for the ~0.1 % of
-// directions within 2e-5 rad of a zone edge (zone_fast returned -1).
+// directions within 2e-5 rad of a zone edge (zone_fast returned -1).  They start from the RAW
+// gradient and normalise it as NumPy does (float32 sqrt and divisions where magn > 1e-5,
+// mad/Orientator.py:160-163).
+__device__ __forceinline__ void normalise_exact(float& gx, float& gy, float& gz) {
+    const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz)));
+    if (m > 1e-5f) {
+        gx = __fdiv_rn(gx, m);
+        gy = __fdiv_rn(gy, m);
+        gz = __fdiv_rn(gz, m);
+    }
+}
 // Unrotated patch: float32 angles against float64 bounds (mad/Orientator.py:305-334 under NumPy 2).
 __device__ __noinline__ void vote_exact_f32(ZoneTab T, float gx, float gy, float gz, int* hist) {
+    normalise_exact(gx, gy, gz);
     float th = (float)atan2((double)gy, (double)gx);
     if (th < 0.f) th = __fadd_rn(th, 6.2831855f);
     const float sth = __fadd_rn(th, 6.2831855f);
@@ -36,6 +47,7 @@ __device__ __noinline__ void vote_exact_f32(ZoneTab T, float gx, float gy, float
 }
 // Rotated patch: float64 throughout (the rotation matrix is float64).
 __device__ __noinline__ void vote_exact_f64(ZoneTab T, const double* __restrict__ R, float gx, float gy, float gz, int* hist) {
+    normalise_exact(gx, gy, gz);
     const double px = gx, py = gy, pz = gz;
     const double vx = fma(pz, R[2], fma(py, R[1], px * R[0]));
     const double vy = fma(pz, R[5], fma(py, R[4], px * R[3]));
@@ -50,17 +62,35 @@ __device__ __noinline__ void vote_exact_f64(ZoneTab T, const double* __restrict_
     if (nzn > 1) atomicAdd(&hist[z[1]], 1);
 }
 
+// Ordered compaction of the zones [lo, hi) whose flag is set into out[0..8) (ascending zone index, as
+// the reference's np.where); returns the total count.  Called by all 128 threads (4 warps).
+__device__ __forceinline__ int select_zones(bool flag, int zone, int* out, int* warp_cnt) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, flag);
+    if (lane == 0) warp_cnt[warp] = __popc(m);
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < 4; ++w) { const int c = warp_cnt[w]; if (w < warp) base += c; total += c; }
+    if (flag) {
+        const int p = base + __popc(m & ((1u << lane) - 1u));
+        if (p < 8) out[p] = zone;
+    }
+    __syncthreads();
+    return total;
+}
+
 __global__ void __launch_bounds__(128)
 orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1, OctDims dims,
               const MadKeypoint* __restrict__ kp, int r, const char4* __restrict__ mask_off, int n_mask,
               ZoneTab T, const double* __restrict__ r1_table, int lim_main, int lim_sec,
               int32_t* __restrict__ n_ori, int32_t* __restrict__ slots) {
-    extern __shared__ float4 pv[];     // [n_mask] normalised gradient (x, y, z, weight)
+    extern __shared__ float4 pv[];     // [n_mask] RAW gradient (x, y, z) + w: 1/|g| (fast normalisation),
+                                       //          0 = no vote (|g| < 1e-5), -1 = |g| == 1e-5 exactly (exact path only)
     __shared__ int hist[128];
     __shared__ int hn0[128];
     __shared__ int cur[128];
-    __shared__ int s_main[8];
-    __shared__ int s_nmain, s_hmax, s_count;
+    __shared__ int s_main[8], s_sec[8], s_wcnt[4];
+    __shared__ int s_hmax, s_count;
     __shared__ ZoneFast F;
 
     const int tid = threadIdx.x;
@@ -78,7 +108,7 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
         return;
     }
     if (tid < 128) { hist[tid] = 0; }
-    if (tid == 0) { s_hmax = 0; s_count = 0; s_nmain = 0; }
+    if (tid == 0) { s_hmax = 0; s_count = 0; }
     zone_fast_init(&F, T);
     __syncthreads();
 
@@ -97,28 +127,25 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
             }
         }
         int zf[GB];
-        bool vote[GB];
 #pragma unroll
         for (int u = 0; u < GB; ++u) {                 // branch-free: the GB chains interleave
-            const int i = i0 + u * blockDim.x;
             float4 g = gv[u];
-            const float m = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z)));
-            const float d = (m > 1e-5f) ? m : 1.f;     // normalise where magn > 1e-5 (mad/Orientator.py:160-163)
-            g.x = __fdiv_rn(g.x, d);
-            g.y = __fdiv_rn(g.y, d);
-            g.z = __fdiv_rn(g.z, d);
-            g.w = (m < 1e-5f) ? 0.f : 1.f;
+            // squared magnitude with NumPy's float32 rounding; the 1e-5 cut-offs are decided exactly on it
+            const float m2 = __fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z));
+            const float rinv = rsqrtf(fmaxf(m2, 1e-30f));
+            g.w = (m2 < MAD_M2_LT) ? 0.f : ((m2 >= MAD_M2_GT) ? rinv : -1.f);
             gv[u] = g;
-            vote[u] = (i < n_mask) && (g.w != 0.f);
-            zf[u] = zone_fast(F, g.x, g.y, g.z);
+            zf[u] = (g.w > 0.f) ? zone_fast(F, g.x * rinv, g.y * rinv, g.z * rinv) : -1;
         }
 #pragma unroll
         for (int u = 0; u < GB; ++u) {
             const int i = i0 + u * blockDim.x;
-            if (i < n_mask) pv[i] = gv[u];
-            if (vote[u]) {
-                if (zf[u] >= 0) atomicAdd(&hist[zf[u]], 1);
-                else vote_exact_f32(T, gv[u].x, gv[u].y, gv[u].z, hist);
+            if (i < n_mask) {
+                pv[i] = gv[u];
+                if (gv[u].w != 0.f) {
+                    if (zf[u] >= 0) atomicAdd(&hist[zf[u]], 1);
+                    else vote_exact_f32(T, gv[u].x, gv[u].y, gv[u].z, hist);
+                }
             }
         }
     }
@@ -132,14 +159,8 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
     }
     if (tid < T.n_zones) hn0[tid] = norm50(hist[tid], hmax0);
     __syncthreads();
-    if (tid == 0) {
-        int nm = 0;
-        for (int a = 0; a < T.n_zones; ++a)
-            if (hn0[a] > 40) { if (nm < 8) s_main[nm] = a; ++nm; }   // > max(hn)*0.8 with max(hn) == 50
-        s_nmain = nm;
-    }
-    __syncthreads();
-    const int nmain = s_nmain;
+    // main candidates: zones with > max(hn) * 0.8 where max(hn) == 50, in ascending order
+    const int nmain = select_zones(tid < T.n_zones && hn0[tid] > 40, tid, s_main, s_wcnt);
     if (nmain > lim_main) {
         if (tid == 0) n_ori[ki] = 0;
         return;
@@ -165,9 +186,10 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
                     const int i = min(i0 + u * (int)blockDim.x, n_mask - 1);
                     const float4 g = pv[i];
                     gq[u] = g;
-                    zq[u] = zone_fast(F, fmaf(g.z, rf[2], fmaf(g.y, rf[1], g.x * rf[0])),
-                                      fmaf(g.z, rf[5], fmaf(g.y, rf[4], g.x * rf[3])),
-                                      fmaf(g.z, rf[8], fmaf(g.y, rf[7], g.x * rf[6])));
+                    const float vx = fmaf(g.z, rf[2], fmaf(g.y, rf[1], g.x * rf[0])) * g.w;
+                    const float vy = fmaf(g.z, rf[5], fmaf(g.y, rf[4], g.x * rf[3])) * g.w;
+                    const float vz = fmaf(g.z, rf[8], fmaf(g.y, rf[7], g.x * rf[6])) * g.w;
+                    zq[u] = (g.w > 0.f) ? zone_fast(F, vx, vy, vz) : -1;
                 }
 #pragma unroll
                 for (int u = 0; u < GB; ++u) {
@@ -186,22 +208,19 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
         } else {
             if (tid < T.n_zones) cur[tid] = hn0[tid];
         }
+        __syncthreads();                    // every thread has read s_hmax / written cur
+        if (tid == 0) s_hmax = 0;
         __syncthreads();
-        // ---- step04/05: secondary zones among 1..n_zones-2 ----
-        if (tid == 0 && have) {
-            int qmax = 0;
-            for (int b = 1; b < T.n_zones - 1; ++b) qmax = max(qmax, cur[b]);
-            if (qmax > 0) {
-                int ns = 0;
-                int sec[8];
-                for (int b = 1; b < T.n_zones - 1; ++b)
-                    if (norm50(cur[b], qmax) > 40) { if (ns < 8) sec[ns] = b; ++ns; }
-                if (ns <= lim_sec) {
-                    int c = s_count;
-                    for (int q = 0; q < ns && c < MAD_MAX_ORI; ++q) slots[(long long)ki * MAD_MAX_ORI + c++] = a | (sec[q] << 16);
-                    s_count = c;
-                }
-            }
+        // ---- step04/05: secondary zones among 1..n_zones-2, re-normalised to their own maximum ----
+        const bool inner = tid >= 1 && tid < T.n_zones - 1;
+        if (have && inner) atomicMax(&s_hmax, cur[tid]);
+        __syncthreads();
+        const int qmax = s_hmax;
+        const int ns = select_zones(have && inner && qmax > 0 && norm50(cur[tid], max(qmax, 1)) > 40, tid, s_sec, s_wcnt);
+        if (tid == 0 && have && qmax > 0 && ns <= lim_sec) {
+            int c = s_count;
+            for (int q = 0; q < ns && c < MAD_MAX_ORI; ++q) slots[(long long)ki * MAD_MAX_ORI + c++] = a | (s_sec[q] << 16);
+            s_count = c;
         }
         __syncthreads();
     }
