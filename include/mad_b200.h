@@ -197,15 +197,16 @@ int mad_exclusive_scan_i32_to_i64(const int32_t* in, int n, int64_t* out, int64_
                                   void* workspace, size_t workspace_bytes, void* stream);
 
 /* One-pass threshold matching on the uint8 tcgen05 kernel (the product path): every pair with
- * cosine > cc is appended, unordered, to cand_key[] = (hi << 32) | lo and cand_dot[] = exact integer
+ * cosine > cc is appended, unordered, to cand_key[] (an opaque sort key) and cand_dot[] = exact integer
  * dot product; *count (device, reset by the call) receives the number of pairs FOUND, which may
  * exceed cap -- then only cap were stored and the caller repeats with a larger buffer.
+ * (cand_key holds hi * lo_rows + lo, the row-major rank of the pair.)
  * mad_match_pairs_finish sorts the n stored candidates by (hi, lo) -- the row-major order of
  * np.where(preds > cc), mad/MaD.py:423-424 -- and evaluates the float64 scores. */
 int mad_match_pairs(const MadDscSet* hi, const MadDscSet* lo, double cc, uint64_t* cand_key, int32_t* cand_dot,
                     uint64_t cap, uint64_t* count, void* stream);
 size_t mad_match_pairs_finish_workspace_bytes(long long n);
-int mad_match_pairs_finish(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows,
+int mad_match_pairs_finish(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows, int lo_rows,
                            const int32_t* hi_n2, const int32_t* lo_n2, int32_t* pair_hi, int32_t* pair_lo,
                            double* pair_score, void* workspace, size_t workspace_bytes, void* stream);
 

@@ -61,13 +61,14 @@ dsc_prepare_kernel(const int16_t* __restrict__ dsc, int rows, int rows_padded, i
 }
 
 __global__ void pairs_finish_kernel(const unsigned long long* __restrict__ key, const int32_t* __restrict__ dot,
-                                    long long n, const int32_t* __restrict__ hi_n2, const int32_t* __restrict__ lo_n2,
+                                    long long n, unsigned long long lo_rows, const int32_t* __restrict__ hi_n2,
+                                    const int32_t* __restrict__ lo_n2,
                                     int32_t* __restrict__ pair_hi, int32_t* __restrict__ pair_lo,
                                     double* __restrict__ score) {
     const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (i >= n) return;
     const unsigned long long k = key[i];
-    const int row = (int)(k >> 32), col = (int)(k & 0xFFFFFFFFull);
+    const int row = (int)(k / lo_rows), col = (int)(k % lo_rows);      // key = row * lo_rows + col
     pair_hi[i] = row;
     pair_lo[i] = col;
     score[i] = mad_score(dot[i], (double)__ldg(hi_n2 + row), (double)__ldg(lo_n2 + col));
@@ -129,27 +130,27 @@ extern "C" int mad_match_pairs(const MadDscSet* hi, const MadDscSet* lo, double 
 extern "C" size_t mad_match_pairs_finish_workspace_bytes(long long n) { return finish_layout(n).total; }
 
 extern "C" int mad_match_pairs_finish(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows,
-                                      const int32_t* hi_n2, const int32_t* lo_n2, int32_t* pair_hi, int32_t* pair_lo,
+                                      int lo_rows, const int32_t* hi_n2, const int32_t* lo_n2, int32_t* pair_hi, int32_t* pair_lo,
                                       double* pair_score, void* workspace, size_t workspace_bytes, void* stream) {
     MAD_CHECK_ARG(n >= 0 && n < (1LL << 31));
     if (n == 0) return MAD_OK;
-    MAD_CHECK_ARG(cand_key && cand_dot && hi_n2 && lo_n2 && pair_hi && pair_lo && pair_score && workspace && hi_rows > 0);
+    MAD_CHECK_ARG(cand_key && cand_dot && hi_n2 && lo_n2 && pair_hi && pair_lo && pair_score && workspace && hi_rows > 0 && lo_rows > 0);
     const FinishLayout L = finish_layout(n);
     MAD_CHECK_ARG(workspace_bytes >= L.total);
     cudaStream_t st = (cudaStream_t)stream;
     char* ws = reinterpret_cast<char*>(workspace);
     unsigned long long* key_sorted = reinterpret_cast<unsigned long long*>(ws + L.key_off);
     int32_t* dot_sorted = reinterpret_cast<int32_t*>(ws + L.dot_off);
-    int row_bits = 1;
-    while ((1LL << row_bits) < hi_rows) ++row_bits;
+    int key_bits = 1;                                               // keys are < hi_rows * lo_rows
+    while (key_bits < 64 && (1ULL << key_bits) < (unsigned long long)hi_rows * (unsigned long long)lo_rows) ++key_bits;
     size_t b = L.cub_bytes;
     {
         MAD_PROF("cub_radix_sort_pairs", st);
         MAD_CUDA(cub::DeviceRadixSort::SortPairs(ws + L.cub_off, b, reinterpret_cast<const unsigned long long*>(cand_key),
-                                                 key_sorted, cand_dot, dot_sorted, (int)n, 0, 32 + row_bits, st));
+                                                 key_sorted, cand_dot, dot_sorted, (int)n, 0, key_bits, st));
     }
     MAD_PROF("pairs_finish_kernel", st);
-    pairs_finish_kernel<<<(unsigned)mad_ceil_div(n, 256), 256, 0, st>>>(key_sorted, dot_sorted, n, hi_n2, lo_n2, pair_hi,
+    pairs_finish_kernel<<<(unsigned)mad_ceil_div(n, 256), 256, 0, st>>>(key_sorted, dot_sorted, n, (unsigned long long)lo_rows, hi_n2, lo_n2, pair_hi,
                                                                        pair_lo, pair_score);
     MAD_LAUNCH_OK();
     return MAD_OK;

@@ -134,7 +134,7 @@ struct U8Args {
     const float* lo_rnorm;        // 1/sqrt(n2) as float, 0 for zero descriptors; padded to N_pad
     double cc;
     // PAIRS
-    unsigned long long* cand_key; // (row << 32) | col
+    unsigned long long* cand_key; // row * N + col (row-major rank of the pair: few key bits for the radix sort)
     int32_t* cand_dot;
     unsigned long long cap;
     unsigned long long* count;    // device counter (hits found, may exceed cap)
@@ -281,8 +281,8 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 if (i < n) {
                     key = my_key[i];
                     dot = my_dot[i];
-                    const int r = (int)(key >> 32), c = (int)(key & 0xFFFFFFFFull);
-                    if (r < a.M && c < a.N) {
+                    const int r = (int)(key / (unsigned long long)a.N), c = (int)(key % (unsigned long long)a.N);
+                    if (r < a.M) {
                         const double s = mad_score(dot, (double)__ldg(a.hi_n2 + r), (double)__ldg(a.lo_n2 + c));
                         ok = s > a.cc;
                     }
@@ -377,13 +377,13 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                                 thr = (bi[k_last] < 0) ? -1.f : (float)bs[k_last] - 4e-6f;
                             }
                         }
-                    } else {                                         // rnorm is 0 beyond N: padded columns never pass (cc > 0)
-                        const unsigned long long key = ((unsigned long long)(unsigned)row << 32) | (unsigned)col;
+                    } else if (col < a.N) {                          // (rnorm is 0 beyond N: padded columns only pass when cc <= 0)
+                        const unsigned long long key = (unsigned long long)row * (unsigned long long)a.N + (unsigned long long)col;
                         const int p = atomicAdd((int*)my_cnt, 1);
                         if (p < STG) {
                             my_key[p] = key;
                             my_dot[p] = dot;
-                        } else if (col < a.N) {                      // staging full (very dense hits): exact test right here
+                        } else {                                     // staging full (very dense hits): exact test right here
                             const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
                             if (s > a.cc) {
                                 const unsigned long long gp = atomicAdd(a.count, 1ULL);

@@ -413,7 +413,7 @@ def _match_threshold_onepass(hi, lo, cc, dev, st):
     if p:
         ws_bytes = _lib.lib.mad_match_pairs_finish_workspace_bytes(p)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        call("mad_match_pairs_finish", _ptr(cand_key), _ptr(cand_dot), p, hi.rows, _ptr(hi.norm2), _ptr(lo.norm2),
+        call("mad_match_pairs_finish", _ptr(cand_key), _ptr(cand_dot), p, hi.rows, lo.rows, _ptr(hi.norm2), _ptr(lo.norm2),
              _ptr(pair_hi), _ptr(pair_lo), _ptr(score), _ptr(ws), ws_bytes, st)
     return pair_hi[:p], pair_lo[:p], score[:p]
 
