@@ -82,9 +82,11 @@ __device__ double sym3_max_eig(const float Hf[3][3]) {
     return q + 2.0 * p * cos(phi);
 }
 
-// Phase 1: one thread per interior voxel (blockIdx.y = x plane, one 32-bit divide for (y, z)).
+// Phase 1: a thread owns one interior (y, z) column and walks over XS consecutive x planes
+// (blockIdx.y = slab; one 32-bit divide per thread, all loads of a warp coalesced rows).
 // Voxels above the threshold that equal their 3x3x3 maximum are appended as RAW candidates
 // (accepted = -1) with one atomicAdd each -- they are rare (thousands per map).
+constexpr int kDetectSlab = 8;
 __global__ void __launch_bounds__(256)
 detect_peaks_kernel(const float* __restrict__ L, int nx, int ny, int nz, int oct, int border, float thr,
                     MadKeypoint* __restrict__ cand, int cap, int* __restrict__ count) {
@@ -92,28 +94,38 @@ detect_peaks_kernel(const float* __restrict__ L, int nx, int ny, int nz, int oct
     const unsigned plane = (unsigned)iy * (unsigned)iz;
     const unsigned p = blockIdx.x * 256u + threadIdx.x;
     if (p >= plane) return;
-    const int x = (int)blockIdx.y + border;
     const int yy = (int)(p / (unsigned)iz);
     const int y = yy + border, z = (int)(p - (unsigned)yy * (unsigned)iz) + border;
     const long long sy = nz, sx = (long long)ny * nz;
-    const long long c = x * sx + y * sy + z;
-    const float v = __ldg(L + c);
-    if (!(v > thr)) return;
-    for (int dx = -1; dx <= 1; ++dx)
-        for (int dy = -1; dy <= 1; ++dy) {
-            const float* row = L + c + dx * sx + dy * sy;
-            if (__ldg(row - 1) > v || __ldg(row) > v || __ldg(row + 1) > v) return;
+    const int x0 = (int)blockIdx.y * kDetectSlab + border;
+    const int x1 = min(nx - border, x0 + kDetectSlab);
+    float vals[kDetectSlab];
+#pragma unroll
+    for (int q = 0; q < kDetectSlab; ++q) vals[q] = (x0 + q < x1) ? __ldg(L + (x0 + q) * sx + y * sy + z) : 0.f;
+#pragma unroll
+    for (int q = 0; q < kDetectSlab; ++q) {
+        const float v = vals[q];
+        if (!(v > thr)) continue;                      // also skips the padding of the last slab (0 <= thr)
+        const int x = x0 + q;
+        const long long c = x * sx + y * sy + z;
+        bool is_max = true;
+        for (int dx = -1; dx <= 1 && is_max; ++dx)
+            for (int dy = -1; dy <= 1 && is_max; ++dy) {
+                const float* row = L + c + dx * sx + dy * sy;
+                if (__ldg(row - 1) > v || __ldg(row) > v || __ldg(row + 1) > v) is_max = false;
+            }
+        if (!is_max) continue;
+        const int slot = atomicAdd(count, 1);
+        if (slot < cap) {
+            MadKeypoint k;
+            k.vox[0] = x; k.vox[1] = y; k.vox[2] = z;
+            k.oct = oct;
+            k.off[0] = k.off[1] = k.off[2] = 0.f;
+            k.val = v;
+            k.peak[0] = x; k.peak[1] = y; k.peak[2] = z;
+            k.accepted = -1;
+            cand[slot] = k;
         }
-    const int slot = atomicAdd(count, 1);
-    if (slot < cap) {
-        MadKeypoint k;
-        k.vox[0] = x; k.vox[1] = y; k.vox[2] = z;
-        k.oct = oct;
-        k.off[0] = k.off[1] = k.off[2] = 0.f;
-        k.val = v;
-        k.peak[0] = x; k.peak[1] = y; k.peak[2] = z;
-        k.accepted = -1;
-        cand[slot] = k;
     }
 }
 
@@ -226,7 +238,7 @@ extern "C" int mad_detect(const float* log_grid, int nx, int ny, int nz, int oct
     MAD_CHECK_ARG(ix <= 65535);
     cudaStream_t st = (cudaStream_t)stream;
     {
-        dim3 grid_dim((unsigned)mad_ceil_div((long long)iy * iz, 256), (unsigned)ix);
+        dim3 grid_dim((unsigned)mad_ceil_div((long long)iy * iz, 256), (unsigned)mad_ceil_div(ix, kDetectSlab));
         MAD_PROF("detect_peaks_kernel", st);
         detect_peaks_kernel<<<grid_dim, 256, 0, st>>>(log_grid, nx, ny, nz, oct, border, threshold, cand, cap, count);
         MAD_LAUNCH_OK();

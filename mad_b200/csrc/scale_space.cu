@@ -94,6 +94,15 @@ struct GaussStream {
             emit(io, gw);
         }
     }
+    // interior of the line: the window is full, every push emits
+    template <class IO>
+    __device__ __forceinline__ void push_steady(double v, IO& io, const double* gw) {
+#pragma unroll
+        for (int i = 0; i < 2 * GR; ++i) w[i] = w[i + 1];
+        w[2 * GR] = v;
+        ++cnt;
+        emit(io, gw);
+    }
     template <class IO>
     __device__ __forceinline__ void finish(IO& io, const double* gw) {
         if (GR == 0) return;
@@ -106,10 +115,13 @@ struct GaussStream {
 // ring slot of sample i: i mod 48 (48 = chunk + look-ahead; exact for i < 130 000)
 __device__ __forceinline__ int ring_slot(int i) { return i - 48 * ((i * 43691) >> 21); }
 
-template <int GR, class IO>
-__device__ __forceinline__ void spline_line(IO& io, const int n, const SplineParams& prm,
-                                            double* ring, const int rs) {
+template <int GR, int RS, class IO>
+__device__ __forceinline__ void spline_line(IO& io, const int n, const SplineParams& prm, double* ring) {
     constexpr int C = 16, L = 32;
+    constexpr int rs = RS;                         // ring stride in doubles: compile-time, so that the fully
+                                                   // unrolled interior chunk addresses the ring with immediates
+    const double cinf = prm.cprime[39];            // the pivots have converged to 2 - sqrt(3) long before i = 39
+    int b0 = 0;                                    // ring slot of sample s (s is a multiple of 16: 0, 16, 32, 0, ...)
     const int last = n - 3;
     const double M1 = (io.y(0) - 2.0 * io.y(1)) + io.y(2);
     const double Mn2 = (io.y(n - 3) - 2.0 * io.y(n - 2)) + io.y(n - 1);
@@ -119,7 +131,56 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
     double ya = io.y(1), yb = io.y(2);
     GaussStream<GR> gs;
     gs.init();
-    for (int s = 0; s < n; s += C) {
+    for (int s = 0; s < n; s += C, b0 = (b0 == 32) ? 0 : b0 + 16) {
+        if (GR > 0 && s >= 48 && s + 50 < n) {
+            // ---- interior chunk, fully unrolled: no boundary cases, constant pivot, static ring slots ----
+            // invariant on entry: the forward sweep has reached fwd = s + 32 (ring holds x[s .. s+31])
+            double* r0 = ring + b0 * rs;                                  // samples s    .. s+15
+            double* r1 = ring + ((b0 >= 32) ? b0 - 32 : b0 + 16) * rs;    // samples s+16 .. s+31
+            double* r2 = ring + ((b0 >= 16) ? b0 - 16 : b0 + 32) * rs;    // samples s+32 .. s+47
+            {
+                double yy[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) yy[q] = io.y(s + 33 + q);
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    const double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
+                    const double x = (r - xprev) * cinf;
+                    r2[q * rs] = x;
+                    xprev = x;
+                    ya = yb;
+                    yb = yy[q];
+                }
+                fwd += 16;
+            }
+            double M = r2[15 * rs];
+#pragma unroll
+            for (int d = 14; d >= 0; --d) M = fma(-cinf, M, r2[d * rs]);
+#pragma unroll
+            for (int d = 15; d >= 1; --d) M = fma(-cinf, M, r1[d * rs]);
+            const double Me = fma(-cinf, M, r1[0]);                       // M[s+16]
+            M = Me;
+#pragma unroll
+            for (int d = 15; d >= 0; --d) {
+                M = fma(-cinf, M, r0[d * rs]);
+                r0[d * rs] = M;
+            }
+            double yn[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) yn[q] = io.y(s + 1 + q);
+            double yi = io.y(s);
+            double Mi = r0[0];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const double Mn = (q < 15) ? r0[(q < 15 ? q + 1 : 0) * rs] : Me;
+                gs.push_steady(yi, io, prm.gw);
+                gs.push_steady(0.5 * (yi + yn[q]) - (Mi + Mn) * 0.0625, io, prm.gw);
+                Mi = Mn;
+                yi = yn[q];
+            }
+            io.chunk_done();
+            continue;
+        }
         const int e = min(s + C, n);
         const int top = min(e + L - 1, last);
         while (fwd <= top) {  // forward Thomas sweep, loads batched 8 deep to keep HBM requests in flight
@@ -216,7 +277,7 @@ spline_up_strided_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int
     io.yin = in + o * (long long)n * inner + j;
     io.uout = out + o * (long long)(2 * n - 1) * inner + j;
     io.stride = inner;
-    spline_line<GR>(io, n, prm, ring_s + threadIdx.x, blockDim.x);
+    spline_line<GR, 128>(io, n, prm, ring_s + threadIdx.x);
 }
 
 // Lines along the contiguous axis: one warp owns 32 consecutive lines; the input lines are staged
@@ -270,7 +331,7 @@ spline_up_z_kernel(const float* __restrict__ in, double* __restrict__ out, int n
     io.kbase = 0;
     io.cnt = 0;
     (void)npad;
-    spline_line<GR>(io, n, prm, ring + lane, 32);
+    spline_line<GR, 32>(io, n, prm, ring + lane);
 }
 
 static void fill_spline_params(SplineParams& p, const double* gw, int radius) {
@@ -691,32 +752,46 @@ __device__ __forceinline__ float grad_axis(const float* __restrict__ f, long lon
     return __fmul_rn(__fsub_rn(__ldg(f + c + stride), __ldg(f + c - stride)), 0.5f);
 }
 
-// One thread per voxel; blockIdx.y = x plane, blockIdx.x*256 + tid = index inside the (y, z) plane,
-// so the only division is one 32-bit divide by nz.  Loads of a warp are coalesced rows of the
-// x-1 / x+1 planes and the y-1 / y+1 rows (the z neighbours come from L1); the store is one
-// 16-byte (gx, gy, gz, 0) per voxel, 512 contiguous bytes per warp.
+// A thread owns one (y, z) column and marches over XS consecutive x planes (blockIdx.y = slab):
+// the x neighbours travel through registers (prev / cur / next), so every voxel of the Gaussian
+// grid is loaded once for the x and centre terms; the y neighbours are coalesced rows, the z
+// neighbours come from L1.  One 32-bit divide per thread; the store is one 16-byte
+// (gx, gy, gz, 0) per voxel, 512 contiguous bytes per warp.
+constexpr int kGradSlab = 8;
 __global__ void __launch_bounds__(256)
 gradient_kernel(const float* __restrict__ f, int nx, int ny, int nz, float4* __restrict__ grad) {
     const unsigned plane = (unsigned)ny * (unsigned)nz;
     const unsigned p = blockIdx.x * 256u + threadIdx.x;
     if (p >= plane) return;
-    const int x = blockIdx.y;
     const int y = (int)(p / (unsigned)nz);
     const int z = (int)(p - (unsigned)y * (unsigned)nz);
-    const long long c = (long long)x * plane + p;
-    float4 v;
-    v.x = grad_axis(f, c, x, nx, (long long)plane);
-    v.y = grad_axis(f, c, y, ny, nz);
-    v.z = grad_axis(f, c, z, nz, 1);
-    v.w = 0.f;
-    grad[c] = v;
+    const int x0 = blockIdx.y * kGradSlab;
+    const int x1 = min(nx, x0 + kGradSlab);
+    const long long sx = plane;
+    long long c = (long long)x0 * sx + p;
+    float prev = (x0 > 0) ? __ldg(f + c - sx) : 0.f;
+    float cur = __ldg(f + c);
+#pragma unroll 4
+    for (int x = x0; x < x1; ++x, c += sx) {
+        const float next = (x + 1 < nx) ? __ldg(f + c + sx) : 0.f;
+        float4 v;
+        if (x == 0) v.x = __fsub_rn(next, cur);
+        else if (x == nx - 1) v.x = __fsub_rn(cur, prev);
+        else v.x = __fmul_rn(__fsub_rn(next, prev), 0.5f);
+        v.y = grad_axis(f, c, y, ny, nz);
+        v.z = grad_axis(f, c, z, nz, 1);
+        v.w = 0.f;
+        grad[c] = v;
+        prev = cur;
+        cur = next;
+    }
 }
 
 extern "C" int mad_gradient(const float* gauss, int nx, int ny, int nz, float* grad4, void* stream) {
     MAD_CHECK_ARG(gauss && grad4 && nx >= 2 && ny >= 2 && nz >= 2);
     MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad4) & 15) == 0);
     MAD_CHECK_ARG(nx <= 65535 && (long long)ny * nz < (1LL << 31));
-    dim3 grid_dim((unsigned)mad_ceil_div((long long)ny * nz, 256), (unsigned)nx);
+    dim3 grid_dim((unsigned)mad_ceil_div((long long)ny * nz, 256), (unsigned)mad_ceil_div(nx, kGradSlab));
     MAD_PROF("gradient_kernel", stream);
     gradient_kernel<<<grid_dim, 256, 0, (cudaStream_t)stream>>>(gauss, nx, ny, nz, reinterpret_cast<float4*>(grad4));
     MAD_LAUNCH_OK();
