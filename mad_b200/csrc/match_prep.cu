@@ -74,6 +74,11 @@ __global__ void pairs_finish_kernel(const unsigned long long* __restrict__ key, 
     score[i] = mad_score(dot[i], (double)__ldg(hi_n2 + row), (double)__ldg(lo_n2 + col));
 }
 
+// The candidate counter is reset by a kernel, not cudaMemsetAsync: a memset may be routed through a
+// copy engine and then queues behind a large device-to-host copy of another stream (observed: the
+// matching kernel waited 1.4 ms for the descriptor table's copy-out).
+__global__ void zero_u64_kernel(unsigned long long* p) { *p = 0ull; }
+
 struct FinishLayout {
     size_t key_off, dot_off, cub_off, cub_bytes, total;
 };
@@ -111,7 +116,11 @@ extern "C" int mad_match_pairs(const MadDscSet* hi, const MadDscSet* lo, double 
                                uint64_t cap, uint64_t* count, void* stream) {
     MAD_CHECK_ARG(hi && lo && count && hi->rows >= 0 && lo->rows >= 0);
     cudaStream_t st = (cudaStream_t)stream;
-    MAD_CUDA(cudaMemsetAsync(count, 0, sizeof(uint64_t), st));
+    {
+        MAD_PROF("zero_u64_kernel", st);
+        zero_u64_kernel<<<1, 1, 0, st>>>(reinterpret_cast<unsigned long long*>(count));
+        MAD_LAUNCH_OK();
+    }
     if (hi->rows == 0 || lo->rows == 0) return MAD_OK;
     MAD_CHECK_ARG(hi->u8 && lo->u8 && hi->norm2 && lo->norm2 && lo->rnorm && cand_key && cand_dot);
     MAD_CHECK_ARG(hi->rows_padded >= hi->rows && hi->rows_padded % 128 == 0);

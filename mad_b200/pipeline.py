@@ -347,9 +347,20 @@ def _as_set(x):
 
 
 def _pick_impl(hi, lo, impl):
-    """impl None = product choice: the uint8 tcgen05 kernel, or the fp16 one if an entry exceeds 255."""
+    """impl None = product choice: the uint8 tcgen05 kernel, or the fp16 one if an entry exceeds 255.
+    Returns (impl, verify).  When the largest entry of a set has not been read back yet, the uint8
+    kernel runs optimistically and the check is folded into the read-back the call makes anyway
+    (verify = True): a separate 4-byte device-to-host read here would queue behind any large
+    copy-out in flight on another stream and stall the matching kernel for its whole duration."""
+    verify = False
     if impl is None:
-        impl = 0 if max(hi.max_entry, lo.max_entry) <= 255 else 2
+        if hi._max_entry is None or lo._max_entry is None:
+            return 0, True
+        impl = 0 if max(hi._max_entry, lo._max_entry) <= 255 else 2
+    return _pick_impl_explicit(hi, lo, impl), verify
+
+
+def _pick_impl_explicit(hi, lo, impl):
     if impl == 0:
         hi.max_entry, lo.max_entry          # noqa: B018  (fills the C structs)
     if impl == 2:
@@ -373,9 +384,9 @@ def match_threshold(hi, lo, cc=0.6, impl=None):
     if m == 0 or lo.rows == 0:
         e = torch.empty(0, dtype=torch.int32, device=dev)
         return e, e.clone(), torch.empty(0, dtype=torch.float64, device=dev)
-    impl = _pick_impl(hi, lo, impl)
+    impl, verify = _pick_impl(hi, lo, impl)
     if impl == 0:
-        return _match_threshold_onepass(hi, lo, cc, dev, st)
+        return _match_threshold_onepass(hi, lo, cc, dev, st, verify)
     n_seg = int(_lib.lib.mad_match_segments(m, lo.rows, impl))
     seg_count = torch.empty(m * n_seg, dtype=torch.int32, device=dev)
     call("mad_match_count", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), n_seg, _ptr(seg_count), impl, st)
@@ -393,7 +404,15 @@ def match_threshold(hi, lo, cc=0.6, impl=None):
     return pair_hi[:p], pair_lo[:p], score[:p]
 
 
-def _match_threshold_onepass(hi, lo, cc, dev, st):
+def _read_counts(count, hi, lo):
+    """One device->host read: (pairs found, largest entry of hi, of lo); caches the maxima."""
+    vals = torch.cat([count.view(-1), hi._max_dev.to(torch.int64), lo._max_dev.to(torch.int64)]).tolist()
+    hi._max_entry, lo._max_entry = int(vals[1]), int(vals[2])
+    hi.c.max_entry, lo.c.max_entry = hi._max_entry, lo._max_entry
+    return int(vals[0])
+
+
+def _match_threshold_onepass(hi, lo, cc, dev, st, verify=False):
     key = (hi.rows, lo.rows)
     cap = _PAIR_CAP.get(key, max(1 << 20, 16 * (hi.rows + lo.rows)))
     while True:
@@ -402,7 +421,9 @@ def _match_threshold_onepass(hi, lo, cc, dev, st):
         count = torch.empty(1, dtype=torch.int64, device=dev)
         call("mad_match_pairs", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), _ptr(cand_key), _ptr(cand_dot),
              C.c_uint64(cap), _ptr(count), st)
-        p = int(count.item())
+        p = _read_counts(count, hi, lo)
+        if verify and max(hi._max_entry, lo._max_entry) > 255:
+            return match_threshold(hi, lo, cc, impl=2)      # entries above 255: the fp16 tensor-core kernel
         if p <= cap:
             break
         cap = p + p // 8 + 1024            # the candidate list overflowed: repeat with room
@@ -469,13 +490,17 @@ def match_topk(hi, lo, k=8, lo_index_base=0, impl=None):
     hi, lo = _as_set(hi), _as_set(lo)
     dev = hi.dsc.device
     st = _stream()
-    impl = _pick_impl(hi, lo, impl)
+    impl, verify = _pick_impl(hi, lo, impl)
     idx = torch.empty((hi.rows, k), dtype=torch.int32, device=dev)
     score = torch.empty((hi.rows, k), dtype=torch.float64, device=dev)
     ws_bytes = _lib.lib.mad_match_topk_workspace_bytes(hi.rows, lo.rows, int(k), impl)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     call("mad_match_topk", C.byref(hi.c), C.byref(lo.c), int(k), int(lo_index_base), _ptr(idx), _ptr(score), _ptr(ws),
          ws_bytes, impl, st)
+    if verify:
+        _read_counts(torch.zeros(1, dtype=torch.int64, device=dev), hi, lo)
+        if max(hi._max_entry, lo._max_entry) > 255:
+            return match_topk(hi, lo, k, lo_index_base, impl=2)
     return idx, score
 
 
