@@ -36,7 +36,8 @@ constexpr int BN = 128;            // lo rows per tile (UMMA N)
 constexpr int BKB = 128;           // bytes (= uint8 elements) per k-block = one 128-byte swizzle row
 constexpr int UKB = 32;            // UMMA K for 8-bit inputs
 constexpr int KBLOCKS = MAD_DSC_LEN / BKB;          // 8
-constexpr int STAGES = 5;
+constexpr int STAGES = 5;          // one CTA: 5 stages of 128 lo rows (16 KB)
+constexpr int STAGES2 = 10;        // CTA pair: each CTA holds 64 of the 128 lo rows of a stage (8 KB): 10 stages
 constexpr int ACCS = 4;            // TMEM accumulator ring (4 x 128 columns)
 constexpr uint32_t KB_BYTES = BM * BKB;             // 16 KB: one k-block of 128 rows
 constexpr uint32_t A_BYTES = KBLOCKS * KB_BYTES;    // 128 KB resident hi tile
@@ -46,8 +47,8 @@ constexpr uint32_t TMEM_COLS = 512;
 constexpr int STG = 96;            // staged candidates per epilogue warp
 constexpr size_t STG_BYTES = (size_t)EPI_WARPS * STG * (sizeof(unsigned long long) + sizeof(int));
 constexpr size_t RB_BYTES = (size_t)EPI_WARPS * 2 * BN * sizeof(float);   // per-warp, double-buffered 1/|lo| of a tile
-// dynamic smem: [1024 slack][A 128K][B ring 80K][staging 9K][rnorm 4K][barriers, tmem slot, counters 256]
-constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + RB_BYTES + 256;
+// dynamic smem: [1024 slack][A 128K][B ring 80K][staging 9K][rnorm 8K][barriers, tmem slot, counters 512]
+constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + RB_BYTES + 512;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one sm_100 CTA");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -76,6 +77,42 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+// ---- CTA-pair (cta_group::2) variants.  Addresses are the issuing CTA's shared::cta offsets, which are
+// valid shared::cluster addresses of that CTA; clearing bit 24 addresses the same offset in the
+// pair's leader (even) CTA.
+constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load whose bytes are accounted on the LEADER CTA's mbarrier (issued by both CTAs of the pair)
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & kPeerBitMask), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & kPeerBitMask) : "memory");
+}
+// commit that arrives on the barrier at this offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void umma_i8_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -125,6 +162,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
 // kind::i8 instruction descriptor: D = s32 (bits 4-5 = 2), A = B = unsigned 8-bit (format 0), both
 // K-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 constexpr uint32_t kIdesc = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t kIdescPair = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 over the pair
 
 struct U8Args {
     int M, N, S;                  // rows of hi / lo, number of lo segments
@@ -146,45 +184,59 @@ struct U8Args {
 
 enum { MODE_PAIRS = 0, MODE_TOPK = 1, MODE_TOP8 = 2, MODE_PAIRS_RELOAD = 3 };   // TOP8: k <= 8, list in registers
 
-template <int MODE>
+// NCTA = 1: one CTA per 128-row hi tile.  NCTA = 2: a CTA pair (cluster of 2, cta_group::2) owns a
+// 256-row hi tile -- each CTA keeps its own 128 rows resident and loads HALF of every lo stage, the
+// leader issues M=256 MMAs that read both halves: the lo bytes fetched per MMA halve (the one-CTA
+// kernel saturates the L2 -> SM path at ~62 % tensor activity) and the ring holds twice the stages.
+template <int MODE, int NCTA>
 __global__ void __launch_bounds__(THREADS, 1)
 match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, U8Args a) {
+    constexpr int NSTAGE = (NCTA == 2) ? STAGES2 : STAGES;
+    constexpr uint32_t SB = KB_BYTES / NCTA;                       // bytes of a lo stage held by this CTA
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
     uint8_t* gen = smem_raw + (base - raw);
     const uint32_t b_ring = base + A_BYTES;
-    constexpr uint32_t STG_OFF = A_BYTES + STAGES * KB_BYTES;
+    constexpr uint32_t STG_OFF = A_BYTES + STAGES * KB_BYTES;     // (NSTAGE * SB is the same 80 KB)
     unsigned long long* stg_key = reinterpret_cast<unsigned long long*>(gen + STG_OFF);        // [EPI_WARPS][STG]
     int* stg_dot = reinterpret_cast<int*>(gen + STG_OFF + EPI_WARPS * STG * sizeof(unsigned long long));   // [EPI_WARPS][STG]
     float* s_rb = reinterpret_cast<float*>(gen + STG_OFF + (uint32_t)STG_BYTES);                  // [EPI_WARPS][2][BN]
     constexpr uint32_t BAR_OFF = STG_OFF + (uint32_t)(STG_BYTES + RB_BYTES);
     const uint32_t bars = base + BAR_OFF;
     auto full_bar = [&](int s) { return bars + 8u * s; };
-    auto empty_bar = [&](int s) { return bars + 8u * (STAGES + s); };
-    auto tfull_bar = [&](int q) { return bars + 8u * (2 * STAGES + q); };
-    auto tempty_bar = [&](int q) { return bars + 8u * (2 * STAGES + ACCS + q); };
-    const uint32_t a_bar = bars + 8u * (2 * STAGES + 2 * ACCS);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + BAR_OFF + 8 * (2 * STAGES + 2 * ACCS + 1));
-    int* s_cnt = reinterpret_cast<int*>(gen + BAR_OFF + 8 * (2 * STAGES + 2 * ACCS + 2));       // [EPI_WARPS]
+    auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
+    auto tfull_bar = [&](int q) { return bars + 8u * (2 * NSTAGE + q); };
+    auto tempty_bar = [&](int q) { return bars + 8u * (2 * NSTAGE + ACCS + q); };
+    const uint32_t a_bar = bars + 8u * (2 * NSTAGE + 2 * ACCS);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + BAR_OFF + 8 * (2 * NSTAGE + 2 * ACCS + 1));
+    int* s_cnt = reinterpret_cast<int*>(gen + BAR_OFF + 8 * (2 * NSTAGE + 2 * ACCS + 2));       // [EPI_WARPS]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * BM;
+    const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;    // 0 = leader of the pair
+    const int m0 = blockIdx.x * BM;                                // pairs are consecutive blockIdx.x: rows follow
     const int seg = blockIdx.y;
     const int n_tiles_total = (a.N + BN - 1) / BN;
     const int t_begin = seg * a.tiles_per_seg;
     const int t_end = min(n_tiles_total, t_begin + a.tiles_per_seg);
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-        for (int q = 0; q < ACCS; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 4); }
+        for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        // the leader's "accumulator drained" barrier collects the 4 epilogue warps of BOTH CTAs
+        for (int q = 0; q < ACCS; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 4 * NCTA); }
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < EPI_WARPS) s_cnt[threadIdx.x] = 0;
+    if (NCTA == 2) cluster_sync_all();                             // barriers of both CTAs exist before any remote arrive
     if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (NCTA == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TMEM_COLS) : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tc_fence_before();
     __syncthreads();
@@ -194,22 +246,33 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     if (warp == 0) {
         // ===================== TMA producer (one elected lane) =====================
         if (lane == 0) {
-            mbar_expect_tx(a_bar, A_BYTES);
-            for (int kb = 0; kb < KBLOCKS; ++kb) tma_load_2d(base + kb * KB_BYTES, &map_hi, a_bar, kb * BKB, m0);
+            if (NCTA == 2) {
+                // both hi tiles (2 x 128 KB) and both halves of every lo stage are accounted on the LEADER's barriers
+                if (rank == 0) mbar_expect_tx(a_bar, 2 * A_BYTES);
+                for (int kb = 0; kb < KBLOCKS; ++kb) tma_load_2d_2sm(base + kb * KB_BYTES, &map_hi, a_bar, kb * BKB, m0);
+            } else {
+                mbar_expect_tx(a_bar, A_BYTES);
+                for (int kb = 0; kb < KBLOCKS; ++kb) tma_load_2d(base + kb * KB_BYTES, &map_hi, a_bar, kb * BKB, m0);
+            }
             int stage = 0;
             uint32_t phase = 0;
             for (int t = t_begin; t < t_end; ++t) {
                 for (int kb = 0; kb < KBLOCKS; ++kb) {
-                    mbar_wait(empty_bar(stage), phase ^ 1u);
-                    mbar_expect_tx(full_bar(stage), KB_BYTES);
-                    tma_load_2d(b_ring + stage * KB_BYTES, &map_lo, full_bar(stage), kb * BKB, t * BN);
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    mbar_wait(empty_bar(stage), phase ^ 1u);       // own barrier: the pair's commit arrives in both CTAs
+                    if (NCTA == 2) {
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), KB_BYTES);
+                        tma_load_2d_2sm(b_ring + stage * SB, &map_lo, full_bar(stage), kb * BKB, t * BN + (int)rank * (BN / 2));
+                    } else {
+                        mbar_expect_tx(full_bar(stage), KB_BYTES);
+                        tma_load_2d(b_ring + stage * SB, &map_lo, full_bar(stage), kb * BKB, t * BN);
+                    }
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (one thread) =====================
-        if (lane == 0) {
+        if (lane == 0 && rank == 0) {                                // in a pair only the leader issues MMAs
             mbar_wait(a_bar, 0);
             tc_fence_after();
             int stage = 0;
@@ -225,16 +288,19 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
                     const uint64_t da = umma_smem_desc(base + kb * KB_BYTES);
-                    const uint64_t db = umma_smem_desc(b_ring + stage * KB_BYTES);
+                    const uint64_t db = umma_smem_desc(b_ring + stage * SB);
 #pragma unroll
                     for (int kk = 0; kk < BKB / UKB; ++kk) {
                         // advance 32 bytes inside the 128-byte swizzle row: +2 in 16-byte units
-                        umma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), kIdesc, (kb | kk) ? 1u : 0u);
+                        if (NCTA == 2) umma_i8_pair(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), kIdescPair, (kb | kk) ? 1u : 0u);
+                        else umma_i8(d_tmem, da + (uint64_t)(2 * kk), db + (uint64_t)(2 * kk), kIdesc, (kb | kk) ? 1u : 0u);
                     }
-                    umma_commit(empty_bar(stage));                   // smem slot free when these MMAs retire
-                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+                    // smem slot free (in both CTAs of a pair) when these MMAs retire
+                    if (NCTA == 2) umma_commit_pair(empty_bar(stage)); else umma_commit(empty_bar(stage));
+                    if (++stage == NSTAGE) { stage = 0; phase ^= 1u; }
                 }
-                umma_commit(tfull_bar(acc));                         // accumulator complete
+                // accumulator complete (signalled to the epilogues of both CTAs of a pair)
+                if (NCTA == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
             }
         }
     } else if (warp >= 4) {
@@ -399,7 +465,9 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             }
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(acc));             // 4 arrivals free the accumulator
+            if (lane == 0) {                                         // 4 (x2 in a pair) arrivals free the accumulator
+                if (NCTA == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
+            }
         }
         if (!kTop) flush();
         if (kTop && row_ok) {
@@ -416,9 +484,11 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     }
     tc_fence_before();
     __syncthreads();
+    if (NCTA == 2) cluster_sync_all();                             // both CTAs are done with TMEM and each other's barriers
     if (warp == 2) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        if (NCTA == 2) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
     }
 }
 
@@ -439,7 +509,7 @@ EncodeTiledFn get_encode() {
 }
 
 // [rows_padded][1024] uint8 row-major; box = 128 bytes (k) x 128 rows, 128-byte swizzle.
-int make_map(CUtensorMap* map, const void* ptr, int rows_padded) {
+int make_map(CUtensorMap* map, const void* ptr, int rows_padded, int box_rows = BM) {
     EncodeTiledFn enc = get_encode();
     if (!enc) {
         mad_set_error("mad_match: cuTensorMapEncodeTiled is not available from the CUDA driver");
@@ -447,7 +517,7 @@ int make_map(CUtensorMap* map, const void* ptr, int rows_padded) {
     }
     cuuint64_t dims[2] = {(cuuint64_t)MAD_DSC_LEN, (cuuint64_t)rows_padded};
     cuuint64_t strides[1] = {(cuuint64_t)MAD_DSC_LEN};
-    cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)BM};
+    cuuint32_t box[2] = {(cuuint32_t)BKB, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(ptr), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -490,19 +560,56 @@ int mad_match_u8_segments(int M, int N) {
     return (int)best_s;
 }
 
-static int launch_common(const void* hi_u8, int M_pad, const void* lo_u8, int N_pad, CUtensorMap* map_hi, CUtensorMap* map_lo) {
+// CTA pairs are used when there are at least two hi tiles (MAD_MATCH_ONE_CTA=1 forces the one-CTA kernel).
+static int pick_ncta(int M) {
+    static const bool one = getenv("MAD_MATCH_ONE_CTA") != nullptr;
+    return (!one && M > BM) ? 2 : 1;
+}
+
+static int launch_common(const void* hi_u8, int M_pad, const void* lo_u8, int N_pad, int ncta, CUtensorMap* map_hi,
+                         CUtensorMap* map_lo) {
     int rc = check_device();
     if (rc != MAD_OK) return rc;
     rc = make_map(map_hi, hi_u8, M_pad);
     if (rc != MAD_OK) return rc;
-    return make_map(map_lo, lo_u8, N_pad);
+    return make_map(map_lo, lo_u8, N_pad, BN / ncta);              // a CTA of a pair loads half of a lo stage
+}
+
+template <int MODE>
+static int launch_u8(int ncta, int M, int S, const CUtensorMap& map_hi, const CUtensorMap& map_lo, const U8Args& a,
+                     cudaStream_t st) {
+    if (ncta == 2) {
+        auto kern = match_u8_kernel<MODE, 2>;
+        MAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2u * (unsigned)mad_ceil_div(M, 2 * BM), (unsigned)S);
+        cfg.blockDim = dim3(THREADS);
+        cfg.dynamicSmemBytes = SMEM_BYTES;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        MAD_CUDA(cudaLaunchKernelEx(&cfg, kern, map_hi, map_lo, a));
+    } else {
+        auto kern = match_u8_kernel<MODE, 1>;
+        MAD_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
+        dim3 grid((unsigned)mad_ceil_div(M, BM), (unsigned)S);
+        kern<<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
+    }
+    MAD_LAUNCH_OK();
+    return MAD_OK;
 }
 
 int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, int N, int N_pad, const int32_t* hi_n2,
                        const int32_t* lo_n2, const float* lo_rnorm, double cc, unsigned long long* cand_key,
                        int32_t* cand_dot, unsigned long long cap, unsigned long long* count, cudaStream_t st) {
     CUtensorMap map_hi, map_lo;
-    int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, &map_hi, &map_lo);
+    const int ncta = pick_ncta(M);
+    int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, ncta, &map_hi, &map_lo);
     if (rc != MAD_OK) return rc;
     U8Args a = {};
     a.M = M; a.N = N;
@@ -510,40 +617,24 @@ int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, i
     a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN), a.S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = cc;
     a.cand_key = cand_key; a.cand_dot = cand_dot; a.cap = cap; a.count = count;
-    dim3 grid((unsigned)mad_ceil_div(M, BM), (unsigned)a.S);
     static const bool use_select = getenv("MAD_PAIRS_SELECT") != nullptr;    // experiment switch (measurement only)
     MAD_PROF("match_u8_pairs_kernel", st);
-    if (use_select) {
-        MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_PAIRS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        match_u8_kernel<MODE_PAIRS><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
-    } else {
-        MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_PAIRS_RELOAD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        match_u8_kernel<MODE_PAIRS_RELOAD><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
-    }
-    MAD_LAUNCH_OK();
-    return MAD_OK;
+    return use_select ? launch_u8<MODE_PAIRS>(ncta, M, a.S, map_hi, map_lo, a, st)
+                      : launch_u8<MODE_PAIRS_RELOAD>(ncta, M, a.S, map_hi, map_lo, a, st);
 }
 
 int mad_match_u8_topk(const void* hi_u8, int M, int M_pad, const void* lo_u8, int N, int N_pad, const int32_t* hi_n2,
                       const int32_t* lo_n2, const float* lo_rnorm, int S, int k, int lo_index_base, int32_t* topk_idx,
                       double* topk_score, cudaStream_t st) {
     CUtensorMap map_hi, map_lo;
-    int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, &map_hi, &map_lo);
+    const int ncta = pick_ncta(M);
+    int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, ncta, &map_hi, &map_lo);
     if (rc != MAD_OK) return rc;
     U8Args a = {};
     a.M = M; a.N = N; a.S = S;
     a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN), S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = 0.0;
     a.k = k; a.lo_index_base = lo_index_base; a.topk_idx = topk_idx; a.topk_score = topk_score;
-    dim3 grid((unsigned)mad_ceil_div(M, BM), (unsigned)S);
     MAD_PROF("match_u8_topk_kernel", st);
-    if (k <= 8) {
-        MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_TOP8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        match_u8_kernel<MODE_TOP8><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
-    } else {
-        MAD_CUDA(cudaFuncSetAttribute(match_u8_kernel<MODE_TOPK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-        match_u8_kernel<MODE_TOPK><<<grid, THREADS, SMEM_BYTES, st>>>(map_hi, map_lo, a);
-    }
-    MAD_LAUNCH_OK();
-    return MAD_OK;
+    return k <= 8 ? launch_u8<MODE_TOP8>(ncta, M, S, map_hi, map_lo, a, st) : launch_u8<MODE_TOPK>(ncta, M, S, map_hi, map_lo, a, st);
 }
