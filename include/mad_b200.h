@@ -154,7 +154,8 @@ int mad_describe(const float* grad4_oct0, const float* grad4_oct1, const int* di
 /* ---- a15: descriptor matching (mad/MaD.py:416-424) ---------------------------------------------- */
 /* A descriptor set prepared for matching (device pointers; the struct itself lives on the host).
  * norm2: exact integer squared L2 norms.  u8: uint8 copy [rows_padded][1024] (zero rows beyond
- * `rows`, rows_padded a multiple of 128) -- the operand of the tcgen05 kind::i8 kernel, exact while
+ * `rows`, rows_padded a multiple of 128; a multiple of 256 enables the CTA-pair kernel) -- the operand of the
+ * tcgen05 kind::i8 kernel, exact while
  * max_entry <= 255 (true for every patch size <= 24: an entry counts the votes of one sub-block).
  * rnorm: float 1/sqrt(norm2) per padded row (0 for zero rows), the fp32 pre-filter's scale.
  * half: optional fp16 copy for the general tensor-core kernel (impl = 2, entries <= 2048).

@@ -32,7 +32,7 @@
 namespace {
 
 constexpr int BM = 128;            // hi rows per CTA (UMMA M)
-constexpr int BN = 128;            // lo rows per tile (UMMA N)
+constexpr int BN = 128;            // lo rows per tile (UMMA N) of the one-CTA kernel; lo rows PER CTA of a pair's 256-wide tile
 constexpr int BKB = 128;           // bytes (= uint8 elements) per k-block = one 128-byte swizzle row
 constexpr int UKB = 32;            // UMMA K for 8-bit inputs
 constexpr int KBLOCKS = MAD_DSC_LEN / BKB;          // 8
@@ -46,7 +46,7 @@ constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
 constexpr int STG = 96;            // staged candidates per epilogue warp
 constexpr size_t STG_BYTES = (size_t)EPI_WARPS * STG * (sizeof(unsigned long long) + sizeof(int));
-constexpr size_t RB_BYTES = (size_t)EPI_WARPS * 2 * BN * sizeof(float);   // per-warp, double-buffered 1/|lo| of a tile
+constexpr size_t RB_BYTES = (size_t)2 * 2 * 256 * sizeof(float);          // per epilogue group, double-buffered 1/|lo| of a tile
 // dynamic smem: [1024 slack][A 128K][B ring 80K][staging 9K][rnorm 8K][barriers, tmem slot, counters 512]
 constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + RB_BYTES + 512;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one sm_100 CTA");
@@ -162,7 +162,7 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr) {
 // kind::i8 instruction descriptor: D = s32 (bits 4-5 = 2), A = B = unsigned 8-bit (format 0), both
 // K-major, N >> 3 at bits 17-22, M >> 4 at bits 24-28.
 constexpr uint32_t kIdesc = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-constexpr uint32_t kIdescPair = (2u << 4) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256 over the pair
+constexpr uint32_t kIdescPair = (2u << 4) | ((uint32_t)((2 * BN) >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);   // M = 256, N = 256 over the pair
 
 struct U8Args {
     int M, N, S;                  // rows of hi / lo, number of lo segments
@@ -182,7 +182,7 @@ struct U8Args {
     double* topk_score;
 };
 
-enum { MODE_PAIRS = 0, MODE_TOPK = 1, MODE_TOP8 = 2, MODE_PAIRS_RELOAD = 3 };   // TOP8: k <= 8, list in registers
+enum { MODE_PAIRS = 0, MODE_TOPK = 1, MODE_TOP8 = 2 };   // TOP8: k <= 8, list in registers
 
 // NCTA = 1: one CTA per 128-row hi tile.  NCTA = 2: a CTA pair (cluster of 2, cta_group::2) owns a
 // 256-row hi tile -- each CTA keeps its own 128 rows resident and loads HALF of every lo stage, the
@@ -191,8 +191,14 @@ enum { MODE_PAIRS = 0, MODE_TOPK = 1, MODE_TOP8 = 2, MODE_PAIRS_RELOAD = 3 };   
 template <int MODE, int NCTA>
 __global__ void __launch_bounds__(THREADS, 1)
 match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constant__ CUtensorMap map_lo, U8Args a) {
-    constexpr int NSTAGE = (NCTA == 2) ? STAGES2 : STAGES;
-    constexpr uint32_t SB = KB_BYTES / NCTA;                       // bytes of a lo stage held by this CTA
+    // Tile width.  The tensor core re-reads the hi operand from shared memory for every MMA, so with
+    // N = 128 the operand reads (A 4 KB + B 4 KB per 64 clk) plus the TMA writes exceed the 128 B/clk
+    // of shared memory: both 128-wide variants measured 61-62 % tensor activity.  The pair uses
+    // N = 256 (each CTA stages 128 of the 256 lo rows): A is amortised over twice the columns.
+    constexpr int TN = (NCTA == 2) ? 2 * BN : BN;
+    constexpr int NACC = (int)TMEM_COLS / TN;                      // accumulators in TMEM: 4 x 128 or 2 x 256 columns
+    constexpr int NSTAGE = STAGES;
+    constexpr uint32_t SB = KB_BYTES;                              // bytes of a lo stage held by this CTA (128 rows x 128 B)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;                 // SWIZZLE_128B tiles need 1024-byte alignment
@@ -201,13 +207,13 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     constexpr uint32_t STG_OFF = A_BYTES + STAGES * KB_BYTES;     // (NSTAGE * SB is the same 80 KB)
     unsigned long long* stg_key = reinterpret_cast<unsigned long long*>(gen + STG_OFF);        // [EPI_WARPS][STG]
     int* stg_dot = reinterpret_cast<int*>(gen + STG_OFF + EPI_WARPS * STG * sizeof(unsigned long long));   // [EPI_WARPS][STG]
-    float* s_rb = reinterpret_cast<float*>(gen + STG_OFF + (uint32_t)STG_BYTES);                  // [EPI_WARPS][2][BN]
+    float* s_rb = reinterpret_cast<float*>(gen + STG_OFF + (uint32_t)STG_BYTES);                  // [2 groups][2][256]
     constexpr uint32_t BAR_OFF = STG_OFF + (uint32_t)(STG_BYTES + RB_BYTES);
     const uint32_t bars = base + BAR_OFF;
     auto full_bar = [&](int s) { return bars + 8u * s; };
     auto empty_bar = [&](int s) { return bars + 8u * (NSTAGE + s); };
     auto tfull_bar = [&](int q) { return bars + 8u * (2 * NSTAGE + q); };
-    auto tempty_bar = [&](int q) { return bars + 8u * (2 * NSTAGE + ACCS + q); };
+    auto tempty_bar = [&](int q) { return bars + 8u * (2 * NSTAGE + ACCS + q); };   // (ACCS slots reserved, NACC used)
     const uint32_t a_bar = bars + 8u * (2 * NSTAGE + 2 * ACCS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + BAR_OFF + 8 * (2 * NSTAGE + 2 * ACCS + 1));
     int* s_cnt = reinterpret_cast<int*>(gen + BAR_OFF + 8 * (2 * NSTAGE + 2 * ACCS + 2));       // [EPI_WARPS]
@@ -216,14 +222,16 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;    // 0 = leader of the pair
     const int m0 = blockIdx.x * BM;                                // pairs are consecutive blockIdx.x: rows follow
     const int seg = blockIdx.y;
-    const int n_tiles_total = (a.N + BN - 1) / BN;
+    const int n_tiles_total = (a.N + TN - 1) / TN;
     const int t_begin = seg * a.tiles_per_seg;
     const int t_end = min(n_tiles_total, t_begin + a.tiles_per_seg);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < NSTAGE; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         // the leader's "accumulator drained" barrier collects the 4 epilogue warps of BOTH CTAs
-        for (int q = 0; q < ACCS; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), 4 * NCTA); }
+        // one-CTA kernel: a tile is drained by ONE epilogue group (4 warps); pair kernel: by both groups
+        // (each takes 128 of the 256 columns) of both CTAs
+        for (int q = 0; q < NACC; ++q) { mbar_init(tfull_bar(q), 1); mbar_init(tempty_bar(q), NCTA == 2 ? 16 : 4); }
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -260,8 +268,8 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 for (int kb = 0; kb < KBLOCKS; ++kb) {
                     mbar_wait(empty_bar(stage), phase ^ 1u);       // own barrier: the pair's commit arrives in both CTAs
                     if (NCTA == 2) {
-                        if (rank == 0) mbar_expect_tx(full_bar(stage), KB_BYTES);
-                        tma_load_2d_2sm(b_ring + stage * SB, &map_lo, full_bar(stage), kb * BKB, t * BN + (int)rank * (BN / 2));
+                        if (rank == 0) mbar_expect_tx(full_bar(stage), 2 * KB_BYTES);
+                        tma_load_2d_2sm(b_ring + stage * SB, &map_lo, full_bar(stage), kb * BKB, t * TN + (int)rank * BN);
                     } else {
                         mbar_expect_tx(full_bar(stage), KB_BYTES);
                         tma_load_2d(b_ring + stage * SB, &map_lo, full_bar(stage), kb * BKB, t * BN);
@@ -279,11 +287,11 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             uint32_t phase = 0;
             int it = 0;
             for (int t = t_begin; t < t_end; ++t, ++it) {
-                const int acc = it % ACCS;
-                const uint32_t acc_phase = (uint32_t)(it / ACCS) & 1u;
+                const int acc = it % NACC;
+                const uint32_t acc_phase = (uint32_t)(it / NACC) & 1u;
                 mbar_wait(tempty_bar(acc), acc_phase ^ 1u);          // epilogue has drained this accumulator
                 tc_fence_after();
-                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(acc * TN);
                 for (int kb = 0; kb < KBLOCKS; ++kb) {
                     mbar_wait(full_bar(stage), phase);
                     tc_fence_after();
@@ -319,7 +327,6 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         int* my_dot = stg_dot + ew * STG;
         volatile int* my_cnt = s_cnt + ew;
         constexpr bool kTop = (MODE == MODE_TOPK || MODE == MODE_TOP8);
-        constexpr bool kReload = (MODE == MODE_PAIRS_RELOAD);        // candidates re-read from TMEM, one column per step
         constexpr int kList = (MODE == MODE_TOPK) ? MAD_TOPK_MAX : (MODE == MODE_TOP8 ? 8 : 1);
         double bs[kList];
         int bi[kList];
@@ -332,12 +339,12 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         // Candidates that pass the fp32 pre-filter are only STAGED here (two shared-memory stores);
         // the float64 test runs at flush time with the lanes working on 32 candidates in parallel,
         // so its latency (L2 load of the lo norm, DSQRT, DDIV) is not serialised per hit.
-        auto flush = [&]() {
+        int stg_n = 0;                                               // candidates staged by this warp (warp-uniform register)
+        auto flush = [&](int n) {
             // Pass 1: exact float64 test of 32 staged candidates per round, survivors compacted in
             // place (a survivor's slot is never above the slot it was read from).  Pass 2: ONE global
             // atomicAdd reserves the output range, then a coalesced copy.
             __syncwarp();
-            const int n = min((int)*my_cnt, STG);
             int total = 0;
             for (int i0 = 0; i0 < n; i0 += 32) {
                 const int i = i0 + lane;
@@ -371,29 +378,38 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                     if (gb + i < a.cap) { a.cand_key[gb + i] = my_key[i]; a.cand_dot[gb + i] = my_dot[i]; }
             }
             __syncwarp();
-            if (lane == 0) *my_cnt = 0;
-            __syncwarp();
         };
-        float* my_rb = s_rb + ew * 2 * BN;
-        auto stage_rb = [&](int t, int buf) {                        // 128 floats of this tile: lane -> one float4
-            const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.lo_rnorm + (long long)t * BN) + lane);
-            reinterpret_cast<float4*>(my_rb + buf * BN)[lane] = r4;
+        // Work split between the two epilogue groups.  One-CTA kernel (128-wide tiles, 4 accumulators): the
+        // groups alternate tiles.  Pair kernel (256-wide tiles, only 2 accumulators fit TMEM): both groups
+        // drain EVERY tile, each its own 128 columns, so an accumulator is free after half an epilogue.
+        constexpr bool kSplitCols = (NCTA == 2);
+        constexpr int kStep = kSplitCols ? 1 : 2;
+        const int c_lo = kSplitCols ? grp * BN : 0;                  // this group's 128 columns of a tile
+        float* my_rb = s_rb + grp * 2 * 256;                         // shared by the 4 warps of this group
+        const int gt = threadIdx.x - 128 - grp * 128;                // thread index inside the group, 0..127
+        auto stage_rb = [&](int t, int buf) {                        // 128 floats of this tile, one float4 per thread
+            if (gt < BN / 4) {
+                const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.lo_rnorm + (long long)t * TN + c_lo) + gt);
+                reinterpret_cast<float4*>(my_rb + buf * 256)[gt] = r4;
+            }
         };
-        int it = grp;                                                // position of the tile in this CTA's sweep
+        auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
+        const int t_first = t_begin + (kSplitCols ? 0 : grp);
+        int it = kSplitCols ? 0 : grp;                               // position of the tile in this CTA's sweep
         int par = 0;                                                 // which rnorm buffer holds the current tile
-        if (t_begin + grp < t_end) stage_rb(t_begin + grp, 0);
-        for (int t = t_begin + grp; t < t_end; t += 2, it += 2, par ^= 1) {
-            const int acc = it % ACCS;
-            const uint32_t acc_phase = (uint32_t)(it / ACCS) & 1u;
-            const int n0 = t * BN;
-            if (t + 2 < t_end) stage_rb(t + 2, par ^ 1);             // this group's next tile: latency hidden by this tile
-            __syncwarp();
-            const float* rbt = my_rb + par * BN;
+        if (t_first < t_end) stage_rb(t_first, 0);
+        for (int t = t_first; t < t_end; t += kStep, it += kStep, par ^= 1) {
+            const int acc = it % NACC;
+            const uint32_t acc_phase = (uint32_t)(it / NACC) & 1u;
+            const int n0 = t * TN;
+            group_sync();                                            // this tile's norms are staged; the other buffer is free
+            if (t + kStep < t_end) stage_rb(t + kStep, par ^ 1);     // this group's next tile: latency hidden by this tile
+            const float* rbt = my_rb + par * 256 - c_lo;             // indexed by the column inside the tile
             mbar_wait(tfull_bar(acc), acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * BN);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * TN);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BN; c0 += 32) {
+            for (int c0 = c_lo; c0 < c_lo + BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
                 float rb[32];
@@ -416,22 +432,14 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 }
                 // zero row: every score is 0 and ties go to the lowest index -- only the first k columns matter
                 if (kTop && row_ok && ra == 0.f) mask = (bi[MODE == MODE_TOP8 ? 7 : k_last] < 0) ? 0xFFFFFFFFu : 0u;
-                // each lane walks its own (rare) candidates; the value comes out of the registers
-                // through a select tree, so lanes with candidates in different columns run together
-                unsigned any = kReload ? __reduce_or_sync(0xFFFFFFFFu, mask) : mask;
-                while (any) {
-                    const int j = __ffs(any) - 1;
-                    any &= any - 1;
-                    int dot;
-                    if (kReload) {
-                        dot = (int)tmem_ld1(taddr + (uint32_t)(c0 + j));
-                        tmem_ld_wait();
-                        if (!((mask >> j) & 1u)) continue;
-                    } else {
-                        dot = (int)mad_select32(v, j);
-                    }
-                    const int col = n0 + c0 + j;
-                    if (kTop) {
+                if (kTop) {
+                    // each lane walks its own (rare) candidates; the value comes out of the registers
+                    // through a select tree, so lanes with candidates in different columns run together
+                    while (mask) {
+                        const int j = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const int dot = (int)mad_select32(v, j);
+                        const int col = n0 + c0 + j;
                         if (col < a.N) {
                             const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
                             if (MODE == MODE_TOP8) {
@@ -443,24 +451,50 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                                 thr = (bi[k_last] < 0) ? -1.f : (float)bs[k_last] - 4e-6f;
                             }
                         }
-                    } else if (col < a.N) {                          // (rnorm is 0 beyond N: padded columns only pass when cc <= 0)
-                        const unsigned long long key = (unsigned long long)row * (unsigned long long)a.N + (unsigned long long)col;
-                        const int p = atomicAdd((int*)my_cnt, 1);
-                        if (p < STG) {
-                            my_key[p] = key;
-                            my_dot[p] = dot;
-                        } else {                                     // staging full (very dense hits): exact test right here
-                            const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
-                            if (s > a.cc) {
-                                const unsigned long long gp = atomicAdd(a.count, 1ULL);
-                                if (gp < a.cap) { a.cand_key[gp] = key; a.cand_dot[gp] = dot; }
+                    }
+                } else {
+                    // Pairs: no atomics on the hot path.  The warp's candidates of this chunk get consecutive
+                    // staging slots from a shuffle prefix sum; each lane then writes its own (usually <= 1)
+                    // candidates, reading the dot product out of its registers through the select tree.
+                    const int left = a.N - (n0 + c0);                // columns of this chunk that exist (rnorm is 0 beyond N,
+                    if (left < 32) mask &= (left <= 0) ? 0u : ((1u << left) - 1u);   // but cc <= 0 would let padding through)
+                    if (__any_sync(0xFFFFFFFFu, mask != 0u)) {
+                        const int cnt = __popc(mask);
+                        int incl = cnt;
+#pragma unroll
+                        for (int o = 1; o < 32; o <<= 1) {
+                            const int nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+                            if (lane >= o) incl += nb;
+                        }
+                        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
+                        if (stg_n + total > STG) { flush(stg_n); stg_n = 0; }
+                        if (total <= STG) {
+                            int p = stg_n + incl - cnt;
+                            while (mask) {
+                                const int j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                my_key[p] = (unsigned long long)row * (unsigned long long)a.N + (unsigned long long)(n0 + c0 + j);
+                                my_dot[p] = (int)mad_select32(v, j);
+                                ++p;
+                            }
+                            stg_n += total;
+                        } else {                                     // > STG candidates in one 32 x 32 chunk: exact test right here
+                            while (mask) {
+                                const int j = __ffs(mask) - 1;
+                                mask &= mask - 1;
+                                const int dot = (int)mad_select32(v, j);
+                                const int col = n0 + c0 + j;
+                                const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
+                                if (s > a.cc) {
+                                    const unsigned long long gp = atomicAdd(a.count, 1ULL);
+                                    if (gp < a.cap) {
+                                        a.cand_key[gp] = (unsigned long long)row * (unsigned long long)a.N + (unsigned long long)col;
+                                        a.cand_dot[gp] = dot;
+                                    }
+                                }
                             }
                         }
                     }
-                }
-                if (!kTop) {
-                    __syncwarp();
-                    if (*my_cnt >= STG / 2) flush();
                 }
             }
             tc_fence_before();
@@ -469,7 +503,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 if (NCTA == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
             }
         }
-        if (!kTop) flush();
+        if (!kTop) flush(stg_n);
         if (kTop && row_ok) {
             // one partial list per (segment, epilogue group): the host merges 2 S lists
             const long long o = ((long long)(seg * 2 + grp) * a.M + row) * a.k;
@@ -544,10 +578,13 @@ int check_device() {
 
 // Number of lo segments: minimises  waves x (tiles per segment + 1)  -- one CTA per SM (224 KB of
 // shared memory), a CTA costs its lo tiles plus one tile-equivalent for loading the hi tile.
+static int pick_ncta(int M, int N_pad);
+
 int mad_match_u8_segments(int M, int N) {
     if (M <= 0 || N <= 0) return 1;
+    const int tn = pick_ncta(M, 256) == 2 ? 2 * BN : BN;           // tile width of the variant this M gets
     const long long m_tiles = mad_ceil_div(M, BM);
-    const long long n_tiles = mad_ceil_div(N, BN);
+    const long long n_tiles = mad_ceil_div(N, tn);
     const long long sms = mad_sm_count();
     long long best_s = 1, best_cost = -1;
     for (long long s = 1; s <= n_tiles; ++s) {
@@ -561,9 +598,10 @@ int mad_match_u8_segments(int M, int N) {
 }
 
 // CTA pairs are used when there are at least two hi tiles (MAD_MATCH_ONE_CTA=1 forces the one-CTA kernel).
-static int pick_ncta(int M) {
+// (the pair's 256-wide tiles read 1/|lo| in 256-float blocks: the lo set must be padded to 256 rows)
+static int pick_ncta(int M, int N_pad) {
     static const bool one = getenv("MAD_MATCH_ONE_CTA") != nullptr;
-    return (!one && M > BM) ? 2 : 1;
+    return (!one && M > BM && N_pad % 256 == 0) ? 2 : 1;
 }
 
 static int launch_common(const void* hi_u8, int M_pad, const void* lo_u8, int N_pad, int ncta, CUtensorMap* map_hi,
@@ -572,7 +610,8 @@ static int launch_common(const void* hi_u8, int M_pad, const void* lo_u8, int N_
     if (rc != MAD_OK) return rc;
     rc = make_map(map_hi, hi_u8, M_pad);
     if (rc != MAD_OK) return rc;
-    return make_map(map_lo, lo_u8, N_pad, BN / ncta);              // a CTA of a pair loads half of a lo stage
+    (void)ncta;
+    return make_map(map_lo, lo_u8, N_pad, BN);                     // 128 lo rows per CTA and stage in both variants
 }
 
 template <int MODE>
@@ -608,31 +647,29 @@ int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, i
                        const int32_t* lo_n2, const float* lo_rnorm, double cc, unsigned long long* cand_key,
                        int32_t* cand_dot, unsigned long long cap, unsigned long long* count, cudaStream_t st) {
     CUtensorMap map_hi, map_lo;
-    const int ncta = pick_ncta(M);
+    const int ncta = pick_ncta(M, N_pad);
     int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, ncta, &map_hi, &map_lo);
     if (rc != MAD_OK) return rc;
     U8Args a = {};
     a.M = M; a.N = N;
     a.S = mad_match_u8_segments(M, N);
-    a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN), a.S);
+    a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN * ncta), a.S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = cc;
     a.cand_key = cand_key; a.cand_dot = cand_dot; a.cap = cap; a.count = count;
-    static const bool use_select = getenv("MAD_PAIRS_SELECT") != nullptr;    // experiment switch (measurement only)
     MAD_PROF("match_u8_pairs_kernel", st);
-    return use_select ? launch_u8<MODE_PAIRS>(ncta, M, a.S, map_hi, map_lo, a, st)
-                      : launch_u8<MODE_PAIRS_RELOAD>(ncta, M, a.S, map_hi, map_lo, a, st);
+    return launch_u8<MODE_PAIRS>(ncta, M, a.S, map_hi, map_lo, a, st);
 }
 
 int mad_match_u8_topk(const void* hi_u8, int M, int M_pad, const void* lo_u8, int N, int N_pad, const int32_t* hi_n2,
                       const int32_t* lo_n2, const float* lo_rnorm, int S, int k, int lo_index_base, int32_t* topk_idx,
                       double* topk_score, cudaStream_t st) {
     CUtensorMap map_hi, map_lo;
-    const int ncta = pick_ncta(M);
+    const int ncta = pick_ncta(M, N_pad);
     int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, ncta, &map_hi, &map_lo);
     if (rc != MAD_OK) return rc;
     U8Args a = {};
     a.M = M; a.N = N; a.S = S;
-    a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN), S);
+    a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN * ncta), S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = 0.0;
     a.k = k; a.lo_index_base = lo_index_base; a.topk_idx = topk_idx; a.topk_score = topk_score;
     MAD_PROF("match_u8_topk_kernel", st);

@@ -304,7 +304,7 @@ class DescriptorSet(object):
         dev = self.dsc.device
         st = _stream()
         self.rows = self.dsc.shape[0]
-        self.rows_padded = max((self.rows + 127) // 128 * 128, 128)
+        self.rows_padded = max((self.rows + 255) // 256 * 256, 256)      # CTA-pair kernel: 256-row lo tiles
         self.norm2 = torch.empty(max(self.rows, 1), dtype=torch.int32, device=dev)
         self.rnorm = torch.empty(self.rows_padded, dtype=torch.float32, device=dev)
         self.u8 = torch.empty((self.rows_padded, DSC_LEN), dtype=torch.uint8, device=dev)
