@@ -348,13 +348,14 @@ def main():
     total_kernel_ms = sum(sum(v) for v in by_name.values())
     kernels = sorted(((nm, sum(v), len(v)) for nm, v in by_name.items()), key=lambda x: -x[1])
 
-    # algorithmic bytes / ops of ONE launch of each kernel (SURVEY 8d convention).
-    # Kernels launched once per octave: the octave-0 (up grid) launch dominates; its duration is the
-    # larger of the two per step and its bytes are those of V0.
+    # algorithmic bytes / ops of each kernel PER STEP (SURVEY 8d convention): kernels that run
+    # once per octave (or, for the slab-pipelined Y / Z passes, once per slab of x planes) are accounted over all
+    # their launches of a step: bytes of both octaves / summed duration.
     M_hi = hi_all.rows
+    VV = V0 + V1
     alg = {
-        "log_pass_x_kernel": ("hbm", 12 * V0), "log_pass_y_kernel": ("hbm", 20 * V0), "log_pass_z_kernel": ("hbm", 20 * V0),
-        "gradient_kernel": ("hbm", 16 * V0 + 4 * V0), "detect_peaks_kernel": ("hbm", 4 * V0),
+        "log_pass_x_kernel": ("hbm", 12 * VV), "log_pass_y_kernel": ("hbm", 20 * VV), "log_pass_z_kernel": ("hbm", 20 * VV),
+        "gradient_kernel": ("hbm", 16 * VV + 4 * VV), "detect_peaks_kernel": ("hbm", 4 * VV),
         "spline_up_z_kernel": ("hbm", 4 * V1 + 8 * 2 * V1), "spline_up_x_kernel": ("hbm", 8 * 2 * V1 + 8 * 4 * V1),
         "spline_up_y_kernel": ("hbm", 8 * 4 * V1 + 4 * V0), "pad3d_kernel": ("hbm", 4 * n_vox + 4 * V1),
         "orient_kernel": ("hbm", 58956 * K), "describe_kernel": ("hbm", 51200 * D),
@@ -369,17 +370,15 @@ def main():
         if name not in alg or name not in by_name:
             return None
         bound, amount = alg[name]
-        durs = sorted(by_name[name], reverse=True)
-        per_step = max(1, len(durs) // args.steps)
-        big = durs[: max(1, len(durs) // per_step)]          # the octave-0 launches (one per step)
-        avg_ms = float(np.mean(big))
+        step_ms_k = float(sum(by_name[name])) / args.steps
         if bound == "hbm":
-            achieved, pk, unit, src = amount / (avg_ms * 1e-3) / 1e9, hbm_peak, "GB/s", hbm_src
+            achieved, pk, unit, src = amount / (step_ms_k * 1e-3) / 1e9, hbm_peak, "GB/s", hbm_src
         else:
-            achieved, pk, unit, src = amount / (avg_ms * 1e-3) / 1e12, 2.0 * bf16_peak, "TFLOP/s", tc_src
+            achieved, pk, unit, src = amount / (step_ms_k * 1e-3) / 1e12, 2.0 * bf16_peak, "TFLOP/s", tc_src
         return {"bound": bound, "kernel": name, "achieved": achieved, "peak": pk, "unit": unit, "frac": achieved / pk,
-                "traffic": traffic.get(name), "peak_source": src, "algorithmic_per_launch": amount,
-                "avg_launch_ms": avg_ms, "share_of_kernel_time": sum(durs) / total_kernel_ms}
+                "traffic": traffic.get(name), "peak_source": src, "algorithmic_per_step": amount,
+                "launches_per_step": len(by_name[name]) // args.steps, "avg_launch_ms": step_ms_k / max(1, len(by_name[name]) // args.steps),
+                "ms_per_step": step_ms_k, "share_of_kernel_time": sum(by_name[name]) / total_kernel_ms}
 
     roofline = None
     for nm, _, _ in kernels:                                  # dominant kernel = largest share with a model
@@ -390,7 +389,7 @@ def main():
     for nm, _, _ in kernels:
         r = kernel_roofline(nm)
         if r:
-            per_kernel[nm] = {"ms": round(r["avg_launch_ms"], 4), "achieved": round(r["achieved"], 1), "unit": r["unit"],
+            per_kernel[nm] = {"ms": round(r["ms_per_step"], 4), "achieved": round(r["achieved"], 1), "unit": r["unit"],
                               "frac": round(r["frac"], 4)}
     map_bytes = 36 * (V0 + V1) + 58956 * K + 51200 * D
     step_ms = ms / args.steps

@@ -5,6 +5,8 @@
 //   a4  gradient field                         (np.gradient,              :187)
 // All kernels are HBM-bound stencils: marching kernels with register windows for the strided
 // axes (coalesced across the contiguous z index), shared-memory row staging for the z axis.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------
@@ -669,44 +671,55 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
         log_pass_strided_kernel<R, ACC, 0><<<grid_dim, 128, 32 * 1 * 128 * sizeof(float), st>>>(grid, nullptr, P0, Q0, nullptr, nx, inner, inner, seg_len, w);
         MAD_LAUNCH_OK();
     }
-    {
-        const long long inner = nz;
-        const long long lines = (long long)nx * nz;
-        const int seg_len = segs_for(lines, ny);
-        dim3 grid_dim((unsigned)mad_ceil_div(lines, 128), (unsigned)mad_ceil_div(ny, seg_len));
-        MAD_PROF("log_pass_y_kernel", st);
-        log_pass_strided_kernel<R, ACC, 1><<<grid_dim, 128, 32 * 2 * 128 * sizeof(float), st>>>(P0, Q0, P01, Rr, S, ny, inner, lines, seg_len, w);
-        MAD_LAUNCH_OK();
+    // Passes Y and Z are independent per x plane and planes are contiguous, so they CAN run slab by slab through
+    // one small set of intermediates that stays in the 126 MB L2 (MAD_LOG_SLAB = planes per slab).  Measured at
+    // C2 on B200 it loses: 8 planes 13.1 ms/step, 16: 11.4, 48: 10.5 against 10.0 unslabbed -- the passes are bound
+    // by FP64 issue and load latency, not by HBM bytes, and small launches under-fill the machine.  Default: off.
+    const long long plane = (long long)ny * nz;
+    static const long long slab_env = getenv("MAD_LOG_SLAB") ? atoll(getenv("MAD_LOG_SLAB")) : 0;
+    long long slab = slab_env;
+    if (slab <= 0 || slab > nx) slab = nx;
+    const int n_chunks = (nz + 7) / 8;
+    const int rs_in = (n_chunks * 8 + 2 * R + 3) / 4 * 4;
+    const int rs_out = (nz + 3) / 4 * 4;
+    const size_t row_bytes = (size_t)(2 * 3 * rs_in + 2 * rs_out) * sizeof(float);   // double-buffered inputs + outputs
+    // rows per batch: the value (within ~72 KB of shared memory, 3-4 CTAs per SM) that leaves the fewest
+    // idle threads over the rows x chunks work items of a batch (wider CTAs measured slower)
+    const int max_rows = (int)std::max<size_t>(1, std::min<size_t>(32, (72 * 1024) / row_bytes));
+    int rows = 1;
+    double best_eff = -1.0;
+    for (int r = 1; r <= max_rows; ++r) {
+        const long long work = (long long)r * n_chunks;
+        const double eff = (double)work / (double)(mad_ceil_div(work, 128) * 128);
+        if (eff > best_eff + 1e-9) { best_eff = eff; rows = r; }
     }
-    {
-        const long long n_rows = (long long)nx * ny;
-        const int n_chunks = (nz + 7) / 8;
-        const int rs_in = (n_chunks * 8 + 2 * R + 3) / 4 * 4;
-        const int rs_out = (nz + 3) / 4 * 4;
-        const size_t row_bytes = (size_t)(2 * 3 * rs_in + 2 * rs_out) * sizeof(float);   // double-buffered inputs + outputs
-        // rows per batch and threads per CTA: the pair (within ~72 KB of shared memory, 3 CTAs per
-        // SM) that leaves the fewest idle threads over the rows x chunks work items of a batch
-        const int max_rows = (int)std::max<size_t>(1, std::min<size_t>(32, (72 * 1024) / row_bytes));
-        int rows = 1, threads = 128;
-        double best_eff = -1.0;
-        for (int r = 1; r <= max_rows; ++r)
-            for (int th = 128; th <= 128; th += 32) {    // wider CTAs measured slower (fewer resident CTAs to overlap the phases)
-                const long long work = (long long)r * n_chunks;
-                const double eff = (double)work / (double)(mad_ceil_div(work, th) * th);
-                if (eff > best_eff + 1e-9) { best_eff = eff; rows = r; threads = th; }
-            }
-        const size_t smem = rows * row_bytes;
-        if (smem > 200 * 1024) {
-            mad_set_error("mad_log_gauss: z extent %d too long for the shared-memory row stage", nz);
-            return MAD_ERR_ARG;
+    const size_t smem = rows * row_bytes;
+    if (smem > 200 * 1024) {
+        mad_set_error("mad_log_gauss: z extent %d too long for the shared-memory row stage", nz);
+        return MAD_ERR_ARG;
+    }
+    MAD_CUDA(cudaFuncSetAttribute(log_pass_z_kernel<R, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+    const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(216 * 1024) / std::max<size_t>(smem, 1)));
+    for (long long x0 = 0; x0 < nx; x0 += slab) {
+        const int sx = (int)std::min<long long>(slab, nx - x0);
+        const long long off = x0 * plane;
+        {
+            const long long inner = nz;
+            const long long lines = (long long)sx * nz;
+            const int seg_len = segs_for(lines, ny);
+            dim3 grid_dim((unsigned)mad_ceil_div(lines, 128), (unsigned)mad_ceil_div(ny, seg_len));
+            MAD_PROF("log_pass_y_kernel", st);
+            log_pass_strided_kernel<R, ACC, 1><<<grid_dim, 128, 32 * 2 * 128 * sizeof(float), st>>>(P0 + off, Q0 + off, P01, Rr, S, ny, inner, lines, seg_len, w);
+            MAD_LAUNCH_OK();
         }
-        MAD_CUDA(cudaFuncSetAttribute(log_pass_z_kernel<R, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-        const long long n_batches = mad_ceil_div(n_rows, rows);
-        const int ctas_per_sm = (int)std::max<size_t>(1, std::min<size_t>(4, (size_t)(216 * 1024) / std::max<size_t>(smem, 1)));
-        const unsigned grid_z = (unsigned)std::min<long long>(n_batches, (long long)sms * ctas_per_sm);
-        MAD_PROF("log_pass_z_kernel", st);
-        log_pass_z_kernel<R, ACC><<<grid_z, threads, smem, st>>>(P01, Rr, S, log_out, gauss_out, nz, n_rows, rows, rs_in, rs_out, n_batches, scale, w);
-        MAD_LAUNCH_OK();
+        {
+            const long long n_rows = (long long)sx * ny;
+            const long long n_batches = mad_ceil_div(n_rows, rows);
+            const unsigned grid_z = (unsigned)std::min<long long>(n_batches, (long long)sms * ctas_per_sm);
+            MAD_PROF("log_pass_z_kernel", st);
+            log_pass_z_kernel<R, ACC><<<grid_z, 128, smem, st>>>(P01, Rr, S, log_out + off, gauss_out + off, nz, n_rows, rows, rs_in, rs_out, n_batches, scale, w);
+            MAD_LAUNCH_OK();
+        }
     }
     return MAD_OK;
 }
