@@ -80,6 +80,21 @@ int mad_profile_count(void);
 int mad_profile_get(int i, const char** name, float* ms);
 int mad_profile_reset(void);
 
+/* ---- a0: Dmap container operations on the device-resident grid (mad/Dmap.py:49-97) ------------ */
+/* Maximum of the grid.  *out_max_ord (device, 4 bytes) receives an order-preserving integer image
+ * of the float maximum; mad_grid_max_decode (host) turns the value read back into the float. */
+int mad_grid_max(const float* grid, long long n, float* out_max_ord, void* stream);
+float mad_grid_max_decode(unsigned int ord);
+/* In place: v < isovalue -> 0 (mad/Dmap.py:50-54), then, if divide, v / vmax as a correctly rounded
+ * float32 division (mad/Dmap.py:66-67). */
+int mad_threshold_normalise(float* grid, long long n, float isovalue, float vmax, int divide, void* stream);
+/* bbox6 (device int[6]) = min x, y, z and max x, y, z of the non-zero voxels (mad/Dmap.py:77-80);
+ * max < 0 when the grid is all zero. */
+int mad_grid_bbox(const float* grid, int nx, int ny, int nz, int* bbox6, void* stream);
+/* out = np.pad(in[x0:x0+cx, y0:y0+cy, z0:z0+cz], pad)  (mad/Dmap.py:86-97). */
+int mad_crop_pad3d(const float* in, int nx, int ny, int nz, int x0, int y0, int z0, int cx, int cy, int cz,
+                   int pad, float* out, void* stream);
+
 /* ---- a1: zero padding (np.pad, mad/MapSpace.py:117-118) ---------------------------------- */
 int mad_pad3d(const float* in, int nx, int ny, int nz, int pad, float* out, void* stream);
 

@@ -56,6 +56,11 @@ SIGNATURES = {
     "mad_profile_count": (_I, []),
     "mad_profile_get": (_I, [_I, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "mad_profile_reset": (_I, []),
+    "mad_grid_max": (_I, [_P, C.c_longlong, _P, _P]),
+    "mad_grid_max_decode": (C.c_float, [C.c_uint]),
+    "mad_threshold_normalise": (_I, [_P, C.c_longlong, C.c_float, C.c_float, _I, _P]),
+    "mad_grid_bbox": (_I, [_P, _I, _I, _I, _P, _P]),
+    "mad_crop_pad3d": (_I, [_P, _I, _I, _I, _I, _I, _I, _I, _I, _I, _I, _P, _P]),
     "mad_pad3d": (_I, [_P, _I, _I, _I, _I, _P, _P]),
     "mad_upsample_workspace_bytes": (_SZ, [_I, _I, _I]),
     "mad_upsample_presmooth": (_I, [_P, _I, _I, _I, _P, _I, _P, _P, _SZ, _P]),

@@ -249,6 +249,41 @@ def main(which):
         path = os.path.join(GOLD, "pair_match.npz")
         np.savez_compressed(path, **out)
         print("wrote %s  M=%d N=%d pairs=%d" % (path, preds.shape[0], preds.shape[1], len(pairs)))
+    if "dmap" in which:
+        # Dmap container (row a0): the reference's own class on a Situs text file
+        from mad.Dmap import Dmap
+        rng = np.random.default_rng(9)
+        shape = (20, 22, 24)
+        x, y, z = np.meshgrid(*[np.arange(s) for s in shape], indexing="ij")
+        g = np.zeros(shape, dtype=np.float64)
+        for _ in range(5):
+            p = np.array([10, 11, 12]) + rng.integers(-4, 5, size=3)
+            g += np.exp(-((x - p[0]) ** 2 + (y - p[1]) ** 2 + (z - p[2]) ** 2) / 5.0)
+        g -= 0.02                                            # some negative background
+        g[g < 1e-3] *= (np.abs(g[g < 1e-3]) > 5e-3)          # exact zeros around the blob
+        path = os.path.join(WORK, "dmap_case.sit")
+        with open(path, "w") as f:
+            f.write("%f %f %f %f %i %i %i\n\n" % (1.5, -3.0, 4.5, 6.0, shape[0], shape[1], shape[2]))
+            k = 0
+            for zz in range(shape[2]):
+                for yy in range(shape[1]):
+                    for xx in range(shape[0]):
+                        f.write("   %6.6f " % g[xx][yy][zz])
+                        k += 1
+                        if k % 10 == 0:
+                            f.write("\n")
+        out = {"sit_text": np.frombuffer(open(path, "rb").read(), dtype=np.uint8)}
+        for tag, kw in (("a", dict(isovalue=0.3)), ("b", dict(isovalue=0.0, normalize=False, pad=3)), ("c", dict(isovalue=50.0))):
+            d = Dmap(path, **kw)
+            out["%s_ctor" % tag] = np.array(d.grid3d, dtype=np.float32)
+            out["%s_ctor_meta" % tag] = np.array([d.voxsp, d.xi, d.yi, d.zi, d.xb, d.yb, d.zb], dtype=np.float64)
+            d.reduce_void()
+            out["%s_void" % tag] = np.array(d.grid3d, dtype=np.float32)
+            out["%s_void_meta" % tag] = np.array([d.voxsp, d.xi, d.yi, d.zi, d.xb, d.yb, d.zb], dtype=np.float64)
+            d.pad_grid(2)
+            out["%s_pad_meta" % tag] = np.array([d.voxsp, d.xi, d.yi, d.zi, d.xb, d.yb, d.zb], dtype=np.float64)
+        np.savez_compressed(os.path.join(GOLD, "dmap.npz"), **out)
+        print("wrote dmap.npz", {k: v.shape for k, v in out.items()})
     if "c1" in which:
         case_from_atoms("c1", synth.random_walk_atoms(9000, 85.0, 1), 4.0, 1.0, full_dsc=False)
 
