@@ -77,11 +77,11 @@ def cpu_crops(grid, n_crops, side=CPU_SAMPLE_SIDE):
     return [np.ascontiguousarray(grid[x:x + side, y:y + side, z:z + side]) for _, x, y, z in cands[:n_crops]]
 
 
-def cpu_run(grid, voxelsp, procs, steps, warmup):
-    """Each step: `procs` processes describe one 64^3 crop each (the reference is single-threaded
+def cpu_run(grid, voxelsp, procs, steps, warmup, side=CPU_SAMPLE_SIDE):
+    """Each step: `procs` processes describe one side^3 crop each (the reference is single-threaded
     Python; one map per process is its many-core form).  Returns (voxels/s, seconds per step, info)."""
     import multiprocessing as mp
-    crops = cpu_crops(grid, procs)
+    crops = cpu_crops(grid, procs, side)
     while len(crops) < procs:
         crops.append(crops[len(crops) % max(len(crops), 1)])
     jobs = [(c, voxelsp) for c in crops]
@@ -94,7 +94,7 @@ def cpu_run(grid, voxelsp, procs, steps, warmup):
         for _ in range(steps):
             info = pool.map(_cpu_one, jobs)
         dt = time.perf_counter() - t0
-    vox = steps * procs * CPU_SAMPLE_SIDE ** 3
+    vox = steps * procs * side ** 3
     return vox / dt, dt / steps, info
 
 
@@ -105,9 +105,17 @@ def run_reference(args):
     import synth
     grid = synth.assembly_map(**C2)
     procs = max(1, min(os.cpu_count() or 1, 32))
-    value, s_per_step, info = cpu_run(grid, C2["voxelsp"], procs, args.steps, args.warmup)
+    # the sample is sized so that the whole run (steps + warm-up) stays near two minutes: a 64^3 crop per
+    # process takes ~4.6 s on a 16-core host, and the cost scales with the crop volume
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    side = 64
+    for cand in (64, 56, 48, 40, 32):
+        side = cand
+        if 4.6 * (cand / 64.0) ** 3 <= budget:
+            break
+    value, s_per_step, info = cpu_run(grid, C2["voxelsp"], procs, args.steps, args.warmup, side)
     sample = ("%d x %d^3 occupancy-matched crops of the C2 map per step, one process each "
-              "(oracle/mad_oracle.py: NumPy/SciPy port of the reference, incl. matching)" % (procs, CPU_SAMPLE_SIDE))
+              "(oracle/mad_oracle.py: NumPy/SciPy port of the reference, incl. matching)" % (procs, side))
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
@@ -196,8 +204,8 @@ def algorithmic_bytes(name, ctx):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4", "c5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

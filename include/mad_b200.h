@@ -239,6 +239,23 @@ int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, int lo_index
 int mad_topk_merge(const int32_t* idx_in, const double* score_in, int G, int M, int k,
                    int32_t* idx_out, double* score_out, void* stream);
 
+/* ---- next component: per-pair repeatability, mad/MaD.py:426-453 ------------------ */
+/* used[idx[i]] = 1 for every i (which features occur in the pair list). */
+int mad_mark_used(const int32_t* idx, long long n, uint8_t* used, void* stream);
+/* For pair p = (hi, lo): R = inv(Rfinal_lo) . Rfinal_hi; the hi cloud (unique sub-voxel coordinates of the
+ * matched hi anchors, [n_hi_cloud][3]) is moved by q = (c - subv_hi) . R^T + subv_lo and
+ * repeatability = 100 * #{q with a lo-cloud point closer than dist} / n_hi_cloud.
+ * results[p][23] = score, repeatability, lo (index, oct, main), hi (index, oct, main), subv_hi[3], subv_lo[3], R[9]
+ * -- the row layout of the reference (mad/MaD.py:451).  *_meta: int32 [D][4] = index, oct_scale, main_bin, sec_bin.
+ * The lo cloud comes cell-sorted for a uniform grid of cell size dist: lo_sorted [L][3], cell_start [ncell + 1],
+ * near_bits = bitmap of cells whose 27-cell neighbourhood is non-empty; grid_org_host / grid_dims_host (host). */
+int mad_repeatability(const int32_t* pair_hi, const int32_t* pair_lo, const double* pair_score, long long n_pairs,
+                      const double* hi_subv, const double* lo_subv, const int32_t* hi_meta, const int32_t* lo_meta,
+                      const double* rf_table, const double* rf_inv_table, int rf_zones,
+                      const double* hi_cloud, int n_hi_cloud, const double* lo_sorted, const int32_t* cell_start,
+                      const uint32_t* near_bits, const double* grid_org_host, const int* grid_dims_host,
+                      double dist, double* results, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

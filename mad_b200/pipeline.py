@@ -512,3 +512,91 @@ def topk_merge(idx_g, score_g):
     score = torch.empty((m, k), dtype=torch.float64, device=dev)
     call("mad_topk_merge", _ptr(idx_g.contiguous()), _ptr(score_g.contiguous()), g, m, k, _ptr(idx), _ptr(score), _stream())
     return idx, score
+
+
+# ---------------------------------------------------------------------------------------------
+# next component: MaD._match_dsc including its per-pair repeatability loop
+# ---------------------------------------------------------------------------------------------
+class FeatureTable(object):
+    """Oriented + described features of one structure as device tables: descriptors (DescriptorSet),
+    meta int32 [D, 4] = (index, oct_scale, main_bin, sec_bin), sub-voxel map coordinates float64 [D, 3]."""
+
+    def __init__(self, dsc, index, oct_scale, main_bin, sec_bin, subv_map_coords):
+        _require_cuda()
+        self.set = dsc if isinstance(dsc, DescriptorSet) else DescriptorSet(dsc)
+        dev = self.set.dsc.device
+        meta = np.stack([np.asarray(index), np.asarray(oct_scale), np.asarray(main_bin), np.asarray(sec_bin)], 1)
+        self.meta_host = np.ascontiguousarray(meta, dtype=np.int32)
+        self.subv_host = np.ascontiguousarray(subv_map_coords, dtype=np.float64).reshape(-1, 3)
+        assert len(self.meta_host) == self.set.rows == len(self.subv_host)
+        self.meta = torch.from_numpy(self.meta_host).to(dev)
+        self.subv = torch.from_numpy(self.subv_host).to(dev)
+
+    @classmethod
+    def from_features(cls, df_list):
+        """From a list of DensityFeature (the reference's ``lo_dsc_list`` / ``hi_dsc_list``)."""
+        dsc = np.array([df.lin_ar_subeqsp for df in df_list], dtype=np.int16).reshape(-1, DSC_LEN)
+        return cls(dsc, [df.index for df in df_list], [df.oct_scale for df in df_list], [df.main_bin for df in df_list],
+                   [df.sec_bin for df in df_list], np.array([df.subv_map_coords for df in df_list], dtype=np.float64))
+
+
+def _cloud_grid(cloud, cell):
+    """Uniform grid (cell size = the distance threshold) over the lo cloud: cell-sorted points, cell_start,
+    and the bitmap of cells whose 27-cell neighbourhood holds a point.  Host glue (a few thousand points)."""
+    org = cloud.min(0) - cell
+    dims = (np.floor((cloud.max(0) - org) / cell).astype(np.int64) + 2)
+    cidx = np.floor((cloud - org) / cell).astype(np.int64)
+    lin = (cidx[:, 0] * dims[1] + cidx[:, 1]) * dims[2] + cidx[:, 2]
+    order = np.argsort(lin, kind="stable")
+    ncell = int(dims.prod())
+    cell_start = np.zeros(ncell + 1, dtype=np.int32)
+    np.cumsum(np.bincount(lin, minlength=ncell), out=cell_start[1:])
+    occ = np.zeros(tuple(dims), dtype=bool)
+    occ[cidx[:, 0], cidx[:, 1], cidx[:, 2]] = True
+    near = np.zeros_like(occ)
+    p = np.pad(occ, 1)
+    for dx in range(3):
+        for dy in range(3):
+            for dz in range(3):
+                near |= p[dx:dx + dims[0], dy:dy + dims[1], dz:dz + dims[2]]
+    bits = np.packbits(near.reshape(-1), bitorder="little")
+    bits = np.concatenate([bits, np.zeros((-len(bits)) % 4, dtype=np.uint8)]).view(np.uint32)
+    return np.ascontiguousarray(cloud[order]), cell_start, bits, org.astype(np.float64), dims.astype(np.int32)
+
+
+def match_dsc(lo, hi, anchor_dist_thresh=4, cc_threshold=0.65, impl=None):
+    """``MaD._match_dsc`` (mad/MaD.py:414-453) on the device: cosine matching above ``cc_threshold`` and, per pair, the
+    rigid transform R = inv(Rfinal_lo) . Rfinal_hi and the repeatability of the matched hi anchors under it.
+    ``lo`` / ``hi``: FeatureTable.  Returns (results float64 [P, 23] device tensor in the reference's row layout,
+    lo_mapcoords, hi_mapcoords as NumPy arrays)."""
+    dev = hi.set.dsc.device
+    st = _stream()
+    ph, pl, sc = match_threshold(hi.set, lo.set, cc_threshold, impl=impl)
+    p = int(ph.numel())
+    if p == 0:
+        return torch.empty((0, 23), dtype=torch.float64, device=dev), np.zeros((0, 3)), np.zeros((0, 3))
+    used_hi = torch.zeros(hi.set.rows, dtype=torch.uint8, device=dev)
+    used_lo = torch.zeros(lo.set.rows, dtype=torch.uint8, device=dev)
+    call("mad_mark_used", _ptr(ph), p, _ptr(used_hi), st)
+    call("mad_mark_used", _ptr(pl), p, _ptr(used_lo), st)
+    hi_cloud = np.unique(hi.subv_host[used_hi.cpu().numpy().astype(bool)], axis=0)        # mad/MaD.py:427
+    lo_cloud = np.unique(lo.subv_host[used_lo.cpu().numpy().astype(bool)], axis=0)        # mad/MaD.py:428
+    lo_sorted, cell_start, bits, org, dims = _cloud_grid(lo_cloud, float(anchor_dist_thresh))
+    tb = device_tables(dev)
+    d_hi_cloud = torch.from_numpy(np.ascontiguousarray(hi_cloud)).to(dev)
+    d_lo_sorted = torch.from_numpy(lo_sorted).to(dev)
+    d_cell_start = torch.from_numpy(cell_start).to(dev)
+    d_bits = torch.from_numpy(bits.view(np.int32)).to(dev)
+    results = torch.empty((p, 23), dtype=torch.float64, device=dev)
+    call("mad_repeatability", _ptr(ph), _ptr(pl), _ptr(sc), p, _ptr(hi.subv), _ptr(lo.subv), _ptr(hi.meta), _ptr(lo.meta),
+         _ptr(tb.rf), _ptr(tb.rf_inv), tb.ori_zones, _ptr(d_hi_cloud), len(hi_cloud), _ptr(d_lo_sorted), _ptr(d_cell_start),
+         _ptr(d_bits), _dptr(org), _dptr(dims), C.c_double(float(anchor_dist_thresh)), _ptr(results), st)
+    return results, lo_cloud, hi_cloud
+
+
+def match_dsc_lists(lo_dsc_list, hi_dsc_list, anchor_dist_thresh=4, cc_threshold=0.65):
+    """Drop-in for ``MaD._match_dsc(lo_dsc_list, hi_dsc_list, anchor_dist_thresh, cc_threshold)``: same arguments
+    (lists of DensityFeature), same return value (list of 23-vectors, lo cloud, hi cloud)."""
+    res, lo_cloud, hi_cloud = match_dsc(FeatureTable.from_features(lo_dsc_list), FeatureTable.from_features(hi_dsc_list),
+                                        anchor_dist_thresh, cc_threshold)
+    return list(res.cpu().numpy()), lo_cloud, hi_cloud

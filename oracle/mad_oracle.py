@@ -445,3 +445,31 @@ def describe_struct(grid, voxelsp, origin=(0.0, 0.0, 0.0), patch_size=16, map_pa
     if timings is not None:
         timings.update(build_space=t1 - t0, detect=t2 - t1, orient=t3 - t2, describe=t4 - t3)
     return sp, kp, ori, dsc
+
+
+# ---------------------------------------------------------------------------------------------
+# next component: the per-pair loop of MaD._match_dsc, mad/MaD.py:426-453
+# ---------------------------------------------------------------------------------------------
+def match_dsc(lo, hi, anchor_dist_thresh=4, cc_threshold=0.65):
+    """``lo`` / ``hi``: dicts with dsc int16[D,1024], subv float64[D,3], index, oct, main, sec, Rfinal
+    float64[D,3,3].  Returns (results float64[P,23], lo_mapcoords, hi_mapcoords) exactly as
+    mad/MaD.py:416-453 builds them."""
+    from scipy.spatial import cKDTree
+    preds = match_scores(hi["dsc"], lo["dsc"])                                   # :416-420
+    ph, pl = np.where(preds > cc_threshold)                                      # :423-424
+    hi_mapcoords = np.unique(hi["subv"][ph], axis=0)                             # :427
+    lo_mapcoords = np.unique(lo["subv"][pl], axis=0)                             # :428
+    lo_tree = cKDTree(lo_mapcoords)                                              # :431
+    results = []
+    for phi, plo in zip(ph, pl):
+        R = np.dot(np.linalg.inv(lo["Rfinal"][plo]), hi["Rfinal"][phi])          # :438
+        l = hi_mapcoords.shape[0]
+        cur = hi_mapcoords - hi["subv"][phi]
+        cur = np.dot(cur, R.T)                                                   # :443
+        cur = cur + lo["subv"][plo]
+        distances, _ = lo_tree.query(cur, distance_upper_bound=anchor_dist_thresh)   # :447
+        repeatability = 100 * np.count_nonzero(distances < anchor_dist_thresh) / l
+        results.append(np.concatenate([[preds[phi, plo], repeatability, lo["index"][plo], lo["oct"][plo], lo["main"][plo],
+                                        hi["index"][phi], hi["oct"][phi], hi["main"][phi]],
+                                       hi["subv"][phi], lo["subv"][plo], R.flatten()]))   # :451
+    return np.array(results, dtype=np.float64).reshape(-1, 23), lo_mapcoords, hi_mapcoords

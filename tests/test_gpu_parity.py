@@ -417,3 +417,62 @@ def test_c3_size_scale_space_linearity(P):
     keep = ka["val"] * np.float32(0.5) > np.float32(0.05)
     assert len(ka) > 100 and keep.sum() == len(kb)
     assert np.array_equal(ka["vox"][keep], kb["vox"]) and np.array_equal(ka["off"][keep], kb["off"])
+
+
+# ---------------------------------------------------------------------------------------------
+# next component: the per-pair loop of MaD._match_dsc (mad/MaD.py:426-453)
+# ---------------------------------------------------------------------------------------------
+def _feature_table(P, g):
+    return P.FeatureTable(g["dsc"], g["of_index"], g["of_oct"], g["of_main"], g["of_sec"], g["of_subv_map_coords"])
+
+
+def test_match_dsc_loop_equals_reference_results(P):
+    """results[P, 23] of MaD._match_dsc: score, repeatability, (index, octave, main bin) of both features, both
+    sub-voxel coordinates and R = inv(Rfinal_lo) . Rfinal_hi -- against the table the reference produced."""
+    ghi, glo, gm = H.golden("pair_hi"), H.golden("pair_lo"), H.golden("pair_match")
+    res, lo_cloud, hi_cloud = P.match_dsc(_feature_table(P, glo), _feature_table(P, ghi), 4, float(gm["cc"]))
+    res = res.cpu().numpy()
+    ref = gm["results"]
+    assert np.array_equal(lo_cloud, gm["lo_cloud"]) and np.array_equal(hi_cloud, gm["hi_cloud"])
+    assert res.shape == ref.shape
+    assert np.array_equal(res[:, 1], ref[:, 1])                            # repeatability: exact counts
+    assert np.array_equal(res[:, 2:14], ref[:, 2:14])                      # bookkeeping and coordinates
+    assert np.abs(res[:, 0] - ref[:, 0]).max() < 1e-14
+    assert np.abs(res[:, 14:] - ref[:, 14:]).max() < 1e-14                 # rotation (dgemm vs plain sums)
+
+
+def test_match_dsc_loop_against_oracle_on_a_denser_case(P):
+    """A lower threshold gives thousands of pairs and larger clouds (oracle = cKDTree restatement)."""
+    import mad_oracle as mo
+    ghi, glo = H.golden("pair_hi"), H.golden("pair_lo")
+    res, lo_cloud, hi_cloud = P.match_dsc(_feature_table(P, glo), _feature_table(P, ghi), 6.5, 0.5)
+    res = res.cpu().numpy()
+
+    def fd(g):
+        rf = {(int(a), int(b)): m for (a, b), m in zip(g["rfinal_ab"], g["rfinal_mat"])}
+        return dict(dsc=g["dsc"], subv=g["of_subv_map_coords"], index=g["of_index"], oct=g["of_oct"], main=g["of_main"],
+                    sec=g["of_sec"], Rfinal=np.array([rf[(int(a), int(b))] for a, b in zip(g["of_main"], g["of_sec"])]))
+    ores, olo, ohi = mo.match_dsc(fd(glo), fd(ghi), 6.5, 0.5)
+    assert len(ores) > 5000 and res.shape == ores.shape
+    assert np.array_equal(lo_cloud, olo) and np.array_equal(hi_cloud, ohi)
+    flips = np.count_nonzero(res[:, 1] != ores[:, 1])
+    assert flips <= 1e-3 * len(ores)                                        # a distance within 1 ulp of the bound may flip
+    assert np.array_equal(res[:, 2:14], ores[:, 2:14])
+
+
+def test_match_dsc_lists_is_a_drop_in(P):
+    """Same call shape as the reference: lists of DensityFeature in, (list of 23-vectors, clouds) out."""
+    from mad_b200.DensityFeature import DensityFeature
+    ghi, glo, gm = H.golden("pair_hi"), H.golden("pair_lo"), H.golden("pair_match")
+
+    def feats(g):
+        out = []
+        for i in range(len(g["of_index"])):
+            df = DensityFeature()
+            df.set_detector_info(int(g["of_index"][i]), int(g["of_oct"][i]), list(g["of_coords"][i]), None,
+                                 g["of_subv_map_coords"][i], 0.0)
+            df.main_bin, df.sec_bin, df.lin_ar_subeqsp = int(g["of_main"][i]), int(g["of_sec"][i]), g["dsc"][i]
+            out.append(df)
+        return out
+    results, lo_cloud, hi_cloud = P.match_dsc_lists(feats(glo), feats(ghi), cc_threshold=float(gm["cc"]))
+    assert len(results) == len(gm["results"]) and np.array_equal(np.array(results)[:, 1], gm["results"][:, 1])

@@ -108,3 +108,21 @@ def test_oracle_edge_cases():
     a[1, :4] = 3
     p, s = mo.match_threshold(a, a, 0.6)
     assert p.tolist() == [[1, 1]]
+
+
+def _feature_dict(g):
+    rf = {(int(a), int(b)): m for (a, b), m in zip(g["rfinal_ab"], g["rfinal_mat"])}
+    R = np.array([rf[(int(a), int(b))] for a, b in zip(g["of_main"], g["of_sec"])])
+    return dict(dsc=g["dsc"], subv=g["of_subv_map_coords"], index=g["of_index"], oct=g["of_oct"], main=g["of_main"],
+                sec=g["of_sec"], Rfinal=R)
+
+
+def test_oracle_match_dsc_loop_equals_reference():
+    """mad/MaD.py:426-453: the per-pair repeatability loop, against the reference's own `results` table."""
+    import mad_oracle as mo
+    ghi, glo, gm = H.golden("pair_hi"), H.golden("pair_lo"), H.golden("pair_match")
+    res, lo_cloud, hi_cloud = mo.match_dsc(_feature_dict(glo), _feature_dict(ghi), 4, float(gm["cc"]))
+    assert np.array_equal(lo_cloud, gm["lo_cloud"]) and np.array_equal(hi_cloud, gm["hi_cloud"])
+    assert res.shape == gm["results"].shape
+    assert np.array_equal(res[:, 1:14], gm["results"][:, 1:14])            # repeatability, indices, coordinates
+    assert np.abs(res[:, 0] - gm["results"][:, 0]).max() < 1e-14 and np.abs(res[:, 14:] - gm["results"][:, 14:]).max() < 1e-14
