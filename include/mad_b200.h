@@ -256,6 +256,18 @@ int mad_repeatability(const int32_t* pair_hi, const int32_t* pair_lo, const doub
                       const uint32_t* near_bits, const double* grid_org_host, const int* grid_dims_host,
                       double dist, double* results, void* stream);
 
+/* ---- next component: atoms -> density, mad/PDB.py:131-163,215-292 -------------------- */
+/* Mass-weighted trilinear splat of n_atoms points (xyz [n][3], mass [n], float64) into grid [px][py][pz] float64
+ * (zeroed by the call); min_host = lattice-registered minimum corner, margin = 2 + pad (mad/PDB.py:246-285). */
+int mad_density_splat(const double* xyz, const double* mass, int n_atoms, const double* min_host, double voxelsp,
+                      int margin, int px, int py, int pz, double* grid, void* stream);
+/* grid /= max(grid) in float64 (mad/PDB.py:287); the grid must be non-negative; scratch8 = 8 device bytes. */
+int mad_normalise_f64(double* grid, long long n, void* scratch8, void* stream);
+/* "full" 1-D convolution with zero extension along the middle axis of in [outer][n][inner] float64 ->
+ * out [outer][n + 2 radius][inner] (float64, or float32 if out_is_f32); w_dev: 2 radius + 1 device weights. */
+int mad_conv_full_f64(const double* in, long long outer, int n, long long inner, const double* w_dev, int radius,
+                      void* out, int out_is_f32, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

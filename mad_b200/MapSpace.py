@@ -70,15 +70,11 @@ class MapSpace(object):
     def _load(self):
         if self._grid is not None:
             return self._grid, self._origin
-        if self.PDB_mode:
-            try:
-                from mad.PDB import PDB           # the reference's own Python (PDB I/O stays there)
-            except Exception as e:                # pragma: no cover
-                raise RuntimeError("MapSpace PDB mode needs the reference's mad.PDB (atoms -> density stays "
-                                   "Python, BASELINE north_star); pass a map file or MapSpace.from_grid") from e
-            grid, xi, yi, zi = PDB(self.structure_file).structure_to_density(self.resolution, self.voxelsp,
-                                                                             isovalue=self.isovalue)
-            return np.asarray(grid, dtype=np.float32), (xi, yi, zi)
+        if self.PDB_mode:                                     # mad/MapSpace.py:73-76: simulated density of the structure
+            from .PDB import PDB
+            grid, xi, yi, zi = PDB(self.structure_file).structure_to_density_device(self.resolution, self.voxelsp,
+                                                                                    isovalue=self.isovalue)
+            return grid, (xi, yi, zi)
         if self.ext in [".situs", ".sit"]:
             with open(self.structure_file, "r") as sit:
                 header = sit.readline().replace("\n", "").replace("  ", "").split(" ")

@@ -88,6 +88,9 @@ SIGNATURES = {
     "mad_match_topk_workspace_bytes": (_SZ, [_I, _I, _I, _I]),
     "mad_match_topk": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), _I, _I, _P, _P, _P, _SZ, _I, _P]),
     "mad_topk_merge": (_I, [_P, _P, _I, _I, _I, _P, _P, _P]),
+    "mad_density_splat": (_I, [_P, _P, _I, _P, C.c_double, _I, _I, _I, _I, _P, _P]),
+    "mad_normalise_f64": (_I, [_P, C.c_longlong, _P, _P]),
+    "mad_conv_full_f64": (_I, [_P, C.c_longlong, _I, C.c_longlong, _P, _I, _P, _I, _P]),
     "mad_mark_used": (_I, [_P, C.c_longlong, _P, _P]),
     "mad_repeatability": (_I, [_P, _P, _P, C.c_longlong, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P,
                                C.c_double, _P, _P]),

@@ -284,6 +284,25 @@ def main(which):
             out["%s_pad_meta" % tag] = np.array([d.voxsp, d.xi, d.yi, d.zi, d.xb, d.yb, d.zb], dtype=np.float64)
         np.savez_compressed(os.path.join(GOLD, "dmap.npz"), **out)
         print("wrote dmap.npz", {k: v.shape for k, v in out.items()})
+    if "density" in which:
+        # atoms -> density: the reference's own PDB.structure_to_density
+        from mad.PDB import PDB
+        coords = synth.random_walk_atoms(300, 30.0, 77)
+        pdb_path = os.path.join(WORK, "density_case.pdb")
+        synth.write_pdb(pdb_path, coords)
+        lines = open(pdb_path).read().splitlines()
+        for i in range(0, len(lines), 7):                       # a few nitrogens / oxygens / one unknown element
+            lines[i] = lines[i][:76] + (" N" if i % 14 else " O")
+        lines[5] = lines[5][:76] + "XX"
+        open(pdb_path, "w").write("\n".join(lines) + "\n")
+        out = {"pdb_text": np.frombuffer(open(pdb_path, "rb").read(), dtype=np.uint8)}
+        for tag, kw in (("a", dict(resolution=8.0, voxelsp=2.0)), ("b", dict(resolution=4.0, voxelsp=1.0, isovalue=0.2)),
+                        ("c", dict(resolution=5.0, voxelsp=2.0, isovalue=0.2, pad=1))):
+            g, dxi, dyi, dzi = PDB(pdb_path).structure_to_density(**kw)
+            out[tag + "_grid"] = g
+            out[tag + "_origin"] = np.array([dxi, dyi, dzi], dtype=np.float64)
+        np.savez_compressed(os.path.join(GOLD, "density.npz"), **out)
+        print("wrote density.npz", {k: v.shape for k, v in out.items()})
     if "c1" in which:
         case_from_atoms("c1", synth.random_walk_atoms(9000, 85.0, 1), 4.0, 1.0, full_dsc=False)
 

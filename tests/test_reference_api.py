@@ -72,3 +72,23 @@ def test_argument_errors_follow_the_reference(tmp_path, capsys):
     with pytest.raises(SystemExit):
         MapSpace("something.txt")                                    # mad/MapSpace.py:63-67
     assert "MaD> ERROR" in capsys.readouterr().out
+
+
+def test_mapspace_pdb_mode_runs_on_the_device(tmp_path):
+    """MapSpace(<pdb>, resolution, voxelsp) (mad/MapSpace.py:73-76): atoms -> density -> scale space without the
+    reference's Python; the density equals the reference's simulation to one float32 ulp (tests/test_density.py)."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from mad_b200.MapSpace import MapSpace
+    from mad_b200.Detector import Detector
+    g = H.golden("density")
+    path = os.path.join(str(tmp_path), "case.pdb")
+    open(path, "wb").write(bytes(g["pdb_text"]))
+    ms = MapSpace(path, resolution=8.0, voxelsp=2.0)
+    ms.build_space()
+    ref = g["a_grid"]
+    assert tuple(ms.space.dims[1]) == tuple(s + 18 for s in ref.shape)
+    assert np.allclose([ms.xi, ms.yi, ms.zi], g["a_origin"] - 9 * 2.0)
+    base = ms.grid_list[1][9:-9, 9:-9, 9:-9]
+    assert np.abs(base - ref).max() <= 1.2e-7
+    assert len(Detector().find_anchors(ms)) > 0
