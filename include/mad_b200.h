@@ -268,6 +268,34 @@ int mad_normalise_f64(double* grid, long long n, void* scratch8, void* stream);
 int mad_conv_full_f64(const double* in, long long outer, int n, long long inner, const double* w_dev, int radius,
                       void* out, int out_is_f32, void* stream);
 
+/* ---- next component: scoring reductions and rigid refinement on HBM-resident grids -------- */
+/* One pass over the common box of two float32 grids [x][y][z]: box_host[9] = (x1, y1, z1, x2, y2, z2, ex, ey, ez), the box
+ * start in each grid and its extent (the bounds of mad/Dmap.py:172-246).  out8 (device float64): [0] sum a b, [1] sum a a,
+ * [2] sum b b, [3] sum a a where b > 0, [4] sum b b where a > 0, [5] #(a > isovalue and b > isovalue), [6] #(a > 0 and
+ * b > 0), [7] 0 -- everything Dmap.get_CCC_with_grid (mad/Dmap.py:248-258), Dmap.get_CCC_with_dmap (:351-372) and
+ * structure_utils.get_overlap (mad/structure_utils.py:254-259) evaluate.  An empty box gives zeros. */
+size_t mad_box_scores_workspace_bytes(int ex, int ey, int ez);
+int mad_box_scores(const float* g1, int nx1, int ny1, int nz1, const float* g2, int nx2, int ny2, int nz2,
+                   const int* box_host, float isovalue, double* out8, void* workspace, size_t workspace_bytes,
+                   void* stream);
+/* *out (device, reset by the call) = #{grid > thr}: np.count_nonzero(grid > isovalue), mad/Dmap.py:354. */
+int mad_grid_count_gt(const float* grid, long long n, float thr, unsigned long long* out, void* stream);
+/* Dmap.mask_with (mad/Dmap.py:99-151): g1 is zeroed outside [lo, hi) on any axis and wherever
+ * g2[x - shift] < 1e-8; shift / lo / hi are the host integers of :115-136. */
+int mad_mask_with(float* g1, int nx1, int ny1, int nz1, const float* g2, int nx2, int ny2, int nz2,
+                  const int* shift_host, const int* lo_host, const int* hi_host, void* stream);
+/* structure_utils.refine_pdb (mad/structure_utils.py:58-161) for n_problems poses of n_atoms atoms each, one CTA per
+ * pose: init [P][n][3] float64 start coordinates, center [P][3] = their mean, max_dist [P] = largest distance from it;
+ * grad4 = mad_gradient of the map (np.gradient, float4 per voxel), px / py / pz = device float64 axis coordinates
+ * (np.arange(o, voxsp n + o, voxsp)[:n]).  Even steps translate along the summed gradient at the atoms (trilinear, as
+ * scipy's RegularGridInterpolator evaluates it), odd steps rotate about the summed torque so that the farthest atom moves
+ * step_size; every 4 steps the step is halved when no atom moved further than it; stops when it drops below min_step.
+ * coords_out [P][n][3] = final coordinates, meta_out [P][4] = (converged, last step index, NaN flag, final step size). */
+int mad_refine_rigid(const float* grad4, int nx, int ny, int nz, const double* px, const double* py, const double* pz,
+                     double voxsp, const double* init, const double* center, const double* max_dist, int n_problems,
+                     int n_atoms, int n_steps, double max_step, double min_step, double* coords_out, double* meta_out,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -4,7 +4,8 @@
 The density simulation (mass-weighted trilinear splat, Gaussian of sigma = resolution / (pi sqrt 2) /
 voxelsp truncated at 3 sigma, max normalisation, isovalue cut) runs in libmad_b200.so; the result can stay
 on the device (``structure_to_density_device``) so that ``MapSpace`` in PDB mode starts from HBM.
-Manipulation helpers of the reference's class (rotate_atoms, rmsd, ...) are downstream Python and not provided.
+The manipulation helpers of the reference's class (rotate_atoms, translate_atoms, rmsd, write_pdb; mad/PDB.py:80-128)
+are host glue with the reference's semantics, used by ``structure_utils``.
 """
 import ctypes as C
 import os
@@ -81,6 +82,33 @@ class PDB(object):
 
     def set_coords(self, coords):
         self.coords = coords.copy()
+
+    def rotate_atoms(self, rot_mat):
+        self.coords = np.dot(self.coords, rot_mat)                         # mad/PDB.py:109-110
+
+    def translate_atoms(self, trans_vec):
+        self.coords += np.array(trans_vec)                                 # mad/PDB.py:112-113
+
+    def get_rmsd_with(self, pdb):
+        d2 = np.square(self.coords - pdb.coords)                           # mad/PDB.py:115-117
+        return np.sqrt(np.sum(d2, axis=(0, 1)) / d2.shape[0])
+
+    def get_rmsdCA_with(self, pdb):
+        if not len(self.CA_idx):                                           # mad/PDB.py:119-128
+            print("PDB> No alpha carbons detected; returning all-atom RMSD instead.")
+            return self.get_rmsd_with(pdb)
+        d2 = np.square(self.coords[self.CA_idx, :] - pdb.coords[pdb.CA_idx, :])
+        return np.sqrt(np.sum(d2, axis=(0, 1)) / d2.shape[0])
+
+    def write_pdb(self, outname):
+        """Fixed-column ATOM / HETATM records, occupancy 1.00, B 0.00 (mad/PDB.py:80-94): 4-letter atom names start
+        one column earlier."""
+        with open(outname, "w") as f:
+            for rec, (x, y, z) in zip(self.info, self.coords):
+                at_num, at_name, res_name, chain_id, res_num, element, line_type = rec
+                name = " %-4s " % at_name if len(at_name) == 4 else "  %-3s " % at_name
+                f.write("%-6s%5i%s%3s%2s%4s    %8.3f%8.3f%8.3f%6.2f%6.2f          %-2s\n"
+                        % (line_type, at_num, name, res_name, chain_id, res_num, x, y, z, 1.0, 0.0, element))
 
     # ---- density ----------------------------------------------------------------------------------
     def _masses(self):

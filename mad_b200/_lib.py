@@ -94,6 +94,12 @@ SIGNATURES = {
     "mad_mark_used": (_I, [_P, C.c_longlong, _P, _P]),
     "mad_repeatability": (_I, [_P, _P, _P, C.c_longlong, _P, _P, _P, _P, _P, _P, _I, _P, _I, _P, _P, _P, _P, _P,
                                C.c_double, _P, _P]),
+    "mad_box_scores_workspace_bytes": (_SZ, [_I, _I, _I]),
+    "mad_box_scores": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P, C.c_float, _P, _P, _SZ, _P]),
+    "mad_grid_count_gt": (_I, [_P, C.c_longlong, C.c_float, _P, _P]),
+    "mad_mask_with": (_I, [_P, _I, _I, _I, _P, _I, _I, _I, _P, _P, _P, _P]),
+    "mad_refine_rigid": (_I, [_P, _I, _I, _I, _P, _P, _P, C.c_double, _P, _P, _P, _I, _I, _I, C.c_double, C.c_double,
+                              _P, _P, _P]),
 }
 
 for _name, (_res, _args) in SIGNATURES.items():

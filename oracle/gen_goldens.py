@@ -303,6 +303,77 @@ def main(which):
             out[tag + "_origin"] = np.array([dxi, dyi, dzi], dtype=np.float64)
         np.savez_compressed(os.path.join(GOLD, "density.npz"), **out)
         print("wrote density.npz", {k: v.shape for k, v in out.items()})
+    if "score" in which:
+        # scoring / refinement numerics: the reference's own Dmap.get_CCC_with_grid,
+        # get_CCC_with_dmap, mask_with, structure_utils.get_overlap and structure_utils.refine_pdb
+        from mad.PDB import PDB
+        from mad.Dmap import Dmap
+        from mad.structure_utils import refine_pdb, get_overlap
+        from mad.math_utils import euler_rod_mat
+
+        def bare_dmap(grid, voxsp, origin):
+            d = Dmap.__new__(Dmap)
+            d.voxsp = voxsp
+            d.xi, d.yi, d.zi = [float(v) for v in origin]
+            d.grid3d = np.array(grid, dtype=np.float32)
+            d.xb, d.yb, d.zb = d.grid3d.shape
+            d.map_name = d.name = "bare"
+            return d
+
+        coords = synth.random_walk_atoms(600, 40.0, 41)
+        pdb_path = os.path.join(WORK, "score_case.pdb")
+        synth.write_pdb(pdb_path, coords)
+        coords = PDB(pdb_path).get_coords().copy()               # as parsed (%8.3f columns)
+        g_map, mxi, myi, mzi = PDB(pdb_path).structure_to_density(8.0, 2.0)
+        g_map = np.pad(g_map, 4)
+        m_org = np.array([mxi - 8.0, myi - 8.0, mzi - 8.0])
+        out = {"pdb_text": np.frombuffer(open(pdb_path, "rb").read(), dtype=np.uint8),
+               "map_grid": np.array(g_map, dtype=np.float32), "map_origin": m_org, "voxsp": np.array(2.0)}
+        # a displaced pose of the same structure and its simulated density
+        cen = coords.mean(0)
+        moved = np.dot(coords - cen, euler_rod_mat(np.array([0.3, -0.5, 0.81]) / np.linalg.norm([0.3, -0.5, 0.81]), 0.12)) \
+            + cen + np.array([2.3, -1.7, 1.1])
+        out["moved"] = moved
+        for tag, kw in (("mad", dict(n_steps=500, max_step_size=1, min_step_size=0.1)), ("default", dict()),
+                        ("short", dict(n_steps=7, max_step_size=1, min_step_size=0.1))):
+            pdb = PDB(pdb_path)
+            pdb.set_coords(moved)
+            t0 = time.perf_counter()
+            rmsd, conv, step = refine_pdb(bare_dmap(g_map, 2.0, m_org), pdb, **kw)
+            dt = time.perf_counter() - t0
+            out["refine_%s_coords" % tag] = pdb.coords.copy()
+            out["refine_%s_meta" % tag] = np.array([rmsd, float(conv), float(step), dt])
+            print("refine", tag, rmsd, conv, step, "%.2fs" % dt,
+                  "rmsd to truth %.4f" % np.sqrt(np.mean(np.sum((pdb.coords - coords) ** 2, axis=1))))
+        pdb = PDB(pdb_path)
+        pdb.set_coords(moved)
+        g_sub, sxi, syi, szi = pdb.structure_to_density(8.0, 2.0)
+        out["sub_grid"] = np.array(g_sub, dtype=np.float32)
+        out["sub_origin"] = np.array([sxi, syi, szi])
+        for tag, iso in (("iso0", 0), ("iso2", 0.2)):
+            d = bare_dmap(g_map, 2.0, m_org)
+            out["ccc_grid_" + tag] = np.array(d.get_CCC_with_grid(g_sub.copy(), sxi, syi, szi, isovalue=iso), dtype=np.float64)
+            d = bare_dmap(g_map, 2.0, m_org)
+            out["ccc_dmap_" + tag] = np.array(d.get_CCC_with_dmap(bare_dmap(g_sub, 2.0, (sxi, syi, szi)), isovalue=iso),
+                                              dtype=np.float64)
+        # a sub grid sticking out of the map on the low side of x and the high side of z, and a disjoint one
+        far = np.array([sxi - 30.0, syi + 4.0, szi + 26.0])
+        out["far_origin"] = far
+        out["ccc_grid_far"] = np.array(bare_dmap(g_map, 2.0, m_org).get_CCC_with_grid(g_sub.copy(), *far), dtype=np.float64)
+        out["ccc_dmap_far"] = np.array(bare_dmap(g_map, 2.0, m_org).get_CCC_with_dmap(bare_dmap(g_sub, 2.0, far)),
+                                       dtype=np.float64)
+        out["overlap"] = np.array(get_overlap([g_map.copy(), *m_org], [g_sub.copy(), sxi, syi, szi], 2), dtype=np.float64)
+        out["overlap_far"] = np.array(get_overlap([g_map.copy(), *m_org], [g_sub.copy(), *far], 2), dtype=np.float64)
+        out["overlap_iso"] = np.array(get_overlap([g_map.copy(), *m_org], [g_sub.copy(), sxi, syi, szi], 2, isovalue=0.3),
+                                      dtype=np.float64)
+        d = bare_dmap(g_map, 2.0, m_org)
+        d.mask_with(bare_dmap(g_sub, 2.0, (sxi, syi, szi)))
+        out["masked"] = d.grid3d.copy()
+        d = bare_dmap(g_map, 2.0, m_org)
+        d.mask_with(bare_dmap(g_sub, 2.0, far))
+        out["masked_far"] = d.grid3d.copy()
+        np.savez_compressed(os.path.join(GOLD, "score.npz"), **out)
+        print("wrote score.npz", {k: (v.shape if v.ndim else float(v)) for k, v in out.items() if k != "pdb_text"})
     if "c1" in which:
         case_from_atoms("c1", synth.random_walk_atoms(9000, 85.0, 1), 4.0, 1.0, full_dsc=False)
 
