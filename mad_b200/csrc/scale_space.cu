@@ -461,6 +461,47 @@ __device__ __forceinline__ float conv_g(const ACC* win, int t, const ConvW& w) {
     return (float)a0;
 }
 
+// Tap-outer forms of the two routines above for T outputs at once: the loop over the taps is outermost, so the T
+// (or 2 T) accumulator chains advance in lock step and every FP64 instruction has T independent neighbours
+// (the per-output summation order is unchanged, hence the same bits).
+template <int R, int T, typename ACC>
+__device__ __forceinline__ void conv_both_rows(const ACC* win, const ConvW& w, float* o0, float* o2) {
+    ACC a0[T], a2[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        a0[t] = win[t + R] * Wt<ACC>::get(w.w0[0]);
+        a2[t] = win[t + R] * Wt<ACC>::get(w.w2[0]);
+    }
+#pragma unroll
+    for (int jj = R; jj >= 1; --jj) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const ACC s = win[t + R - jj] + win[t + R + jj];
+            a0[t] = fma(s, Wt<ACC>::get(w.w0[jj]), a0[t]);
+            a2[t] = fma(s, Wt<ACC>::get(w.w2[jj]), a2[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) { o0[t] = (float)a0[t]; o2[t] = (float)a2[t]; }
+}
+
+template <int R, int T, typename ACC>
+__device__ __forceinline__ void conv_g_rows(const ACC* win, const ConvW& w, float* o0) {
+    ACC a0[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) a0[t] = win[t + R] * Wt<ACC>::get(w.w0[0]);
+#pragma unroll
+    for (int jj = R; jj >= 1; --jj) {
+#pragma unroll
+        for (int t = 0; t < T; ++t) {
+            const ACC s = win[t + R - jj] + win[t + R + jj];
+            a0[t] = fma(s, Wt<ACC>::get(w.w0[jj]), a0[t]);
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < T; ++t) o0[t] = (float)a0[t];
+}
+
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
 }
@@ -645,6 +686,155 @@ log_pass_z_kernel(const float* __restrict__ P01, const float* __restrict__ Rr, c
     cp_async_wait<0>();
 }
 
+// Passes Y and Z fused (one launch per octave instead of two, and no P01 / R / S round trip through HBM:
+// 17 B per voxel instead of 40).  A CTA owns one x plane and a tile of TZ = 128 - 2R z columns plus the R-column
+// halo on either side (reflected at the grid ends): 128 threads, thread t <-> column z0 - R + t.
+//   phase A  every thread marches along y exactly like pass Y above (private cp.async ring, float64 register
+//            windows) and produces T = 8 rows of P01, R, S for its column, rounded to float32 as SciPy stores them
+//            and parked as float64 in a shared-memory stage [3][T][128]; column c of row t sits at
+//            (c & ~7) | ((c & 7) ^ ((7 t + (c >> 4)) & 7)): with u = 14 t + (c >> 3) the 64-bit bank is a bijection of
+//            u mod 16, so the 16 lanes of a half-warp hit 16 different banks both in the column-wise phase-A stores
+//            and in the chunk-strided phase-B window loads;
+//   phase B  T * TZ / 8 work items (row, chunk of 8 z): window of 8 + 2R staged values per array -> Gaussian and the
+//            three Laplacian terms, summed and clamped in float32, written to an output stage;
+//   phase C  the T x TZ output tile goes to HBM as whole row segments (coalesced).
+// Two barriers per T rows; the HBM latency is covered by the cp.async ring as before.
+template <int R, int DEPTH = 32>
+struct YzCfg {
+    static constexpr int T = 8, W = T + 2 * R, D = DEPTH, PF = D / T - 1, G0 = 2 * R / T;
+    static constexpr int TZ = 128 - 2 * R;                      // output columns per CTA
+    static constexpr int CH = TZ / 8;                           // chunks of 8 columns
+    static constexpr int RS = 128;                              // stage row stride in doubles (XOR-swizzled columns)
+    static constexpr int OS = TZ + TZ / 8;                      // output-stage row stride in floats (one pad per chunk)
+    static constexpr size_t ring_bytes = (size_t)D * 2 * 128 * sizeof(float);
+    static constexpr size_t stage_bytes = (size_t)3 * T * RS * sizeof(double);
+    static constexpr size_t out_bytes = (size_t)2 * T * OS * sizeof(float);
+    static constexpr size_t smem = ring_bytes + stage_bytes + out_bytes;
+    static constexpr bool ok = TZ % 8 == 0 && (2 * R) % T == 0 && G0 <= PF + 1;   // R = 4, 8, 12
+};
+
+__device__ __forceinline__ int yz_slot(int row, int col) {
+    return (col & ~7) | ((col & 7) ^ ((7 * row + (col >> 4)) & 7));
+}
+
+template <int R, typename ACC, int MINB, int DEPTH>
+__global__ void __launch_bounds__(128, MINB)
+log_pass_yz_kernel(const float* __restrict__ P0, const float* __restrict__ Q0, float* __restrict__ log_out,
+                   float* __restrict__ gauss_out, int ny, int nz, int n_ztiles, float scale, ConvW w) {
+    using C = YzCfg<R, DEPTH>;
+    static_assert(C::ok, "the fused pass needs a kernel radius that is a multiple of 4");
+    constexpr int T = C::T, W = C::W, D = C::D, PF = C::PF, G0 = C::G0, TZ = C::TZ, CH = C::CH, RS = C::RS, OS = C::OS;
+    extern __shared__ __align__(16) unsigned char yz_smem[];
+    float* ring = reinterpret_cast<float*>(yz_smem);                                    // [D][2][128]
+    double* stage = reinterpret_cast<double*>(yz_smem + C::ring_bytes);                 // [3][T][RS]
+    float* sout = reinterpret_cast<float*>(yz_smem + C::ring_bytes + C::stage_bytes);   // [2][T][TZ]
+    const int tid = threadIdx.x;
+    const int x = blockIdx.x / n_ztiles, zt = blockIdx.x - x * n_ztiles;
+    const int z0 = zt * TZ;
+    int zc = z0 - R + tid;                                       // this thread's column (reflected; clamped when unused)
+    if (zc >= nz + R) zc = nz + R - 1;
+    zc = mad_reflect(zc, nz);
+    const long long plane = (long long)x * ny * nz;
+    const long long base = plane + zc;
+    const int q_end = ny + 2 * R;                                // samples q = y + R in [0, q_end)
+    float* my = ring + tid;
+    auto issue = [&](int grp) {
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const int q = grp * T + i;
+            if (q < q_end) {
+                const long long off = base + (long long)mad_reflect(q - R, ny) * nz;
+                float* dst = my + ((q & (D - 1)) * 2) * 128;
+                cp_async4(dst, P0 + off);
+                cp_async4(dst + 128, Q0 + off);
+            }
+        }
+        cp_async_commit();
+    };
+#pragma unroll
+    for (int grp = 0; grp <= PF; ++grp) issue(grp);
+    cp_async_wait<PF + 1 - G0>();
+    ACC wa[W], wb[W];
+#pragma unroll
+    for (int i = 0; i < 2 * R; ++i) {
+        wa[i] = (ACC)my[(i * 2) * 128];
+        wb[i] = (ACC)my[(i * 2 + 1) * 128];
+    }
+#pragma unroll
+    for (int grp = PF + 1; grp <= PF + G0; ++grp) issue(grp);
+    const int br = tid / CH, bc = tid - br * CH;                 // phase-B work item: row br, chunk bc
+    const bool b_active = tid < T * CH && (z0 + bc * 8) < nz;
+    int grp = G0;
+    for (int a = 0; a < ny; a += T, ++grp) {
+        // ---- phase A: T rows of P01 / R / S for this column
+        cp_async_wait<PF>();
+#pragma unroll
+        for (int i = 0; i < T; ++i) {
+            const int slot = (grp * T + i) & (D - 1);
+            wa[2 * R + i] = (ACC)my[(slot * 2) * 128];
+            wb[2 * R + i] = (ACC)my[(slot * 2 + 1) * 128];
+        }
+        issue(grp + PF + 1);
+        {
+            float r0[T], r2[T], r1[T];
+            conv_both_rows<R, T, ACC>(wa, w, r0, r2);
+            conv_g_rows<R, T, ACC>(wb, w, r1);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const int slot = t * RS + yz_slot(t, tid);
+                stage[0 * T * RS + slot] = (double)r0[t];        // P01 (float32-rounded as SciPy stores it)
+                stage[1 * T * RS + slot] = (double)r2[t];        // R
+                stage[2 * T * RS + slot] = (double)r1[t];        // S
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * R; ++i) {
+            wa[i] = wa[i + T];
+            wb[i] = wb[i + T];
+        }
+        __syncthreads();
+        // ---- phase B: (row, chunk) items from the staged rows
+        const int rows = min(T, ny - a);
+        if (b_active && br < rows) {
+            ACC win[W];
+            auto load_window = [&](int arr) {
+                const double* src = stage + (arr * T + br) * RS;
+#pragma unroll
+                for (int q = 0; q < W; ++q) win[q] = (ACC)src[yz_slot(br, bc * 8 + q)];
+            };
+            float gs[T], t3[T], t2[T], t1[T];
+            load_window(0);
+            conv_both_rows<R, T, ACC>(win, w, gs, t3);
+            load_window(1);
+            conv_g_rows<R, T, ACC>(win, w, t2);
+            load_window(2);
+            conv_g_rows<R, T, ACC>(win, w, t1);
+#pragma unroll
+            for (int t = 0; t < T; ++t) {
+                const float lap = __fadd_rn(__fadd_rn(t1[t], t2[t]), t3[t]);
+                float m = __fmul_rn(-lap, scale);
+                if (m < 0.f) m = 0.f;
+                sout[(0 * T + br) * OS + bc * 9 + t] = m;
+                sout[(1 * T + br) * OS + bc * 9 + t] = gs[t];
+            }
+        }
+        __syncthreads();
+        // ---- phase C: coalesced row segments
+        const int ncol = min(TZ, nz - z0);
+        for (int i = tid; i < rows * TZ; i += 128) {
+            const int r = i / TZ, c = i - r * TZ;
+            if (c < ncol) {
+                const long long off = plane + (long long)(a + r) * nz + z0 + c;
+                log_out[off] = sout[(0 * T + r) * OS + c + (c >> 3)];
+                gauss_out[off] = sout[(1 * T + r) * OS + c + (c >> 3)];
+            }
+        }
+        // the next iteration's first barrier orders these reads of sout before its phase-B writes, and this
+        // iteration's second barrier ordered the phase-B reads of the stage before the next phase-A writes
+    }
+    cp_async_wait<0>();
+}
+
 extern "C" size_t mad_log_gauss_workspace_bytes(int nx, int ny, int nz) {
     const size_t v = mad_align_up((size_t)nx * ny * nz * sizeof(float), 256);
     return 5 * v;  // P0, Q0, P01, R, S
@@ -675,6 +865,20 @@ static int log_gauss_launch(const float* grid, int nx, int ny, int nz, const Con
     // one small set of intermediates that stays in the 126 MB L2 (MAD_LOG_SLAB = planes per slab).  Measured at
     // C2 on B200 it loses: 8 planes 13.1 ms/step, 16: 11.4, 48: 10.5 against 10.0 unslabbed -- the passes are bound
     // by FP64 issue and load latency, not by HBM bytes, and small launches under-fill the machine.  Default: off.
+    // Default: passes Y and Z fused in one launch (MAD_LOG_FUSED=0 selects the two-launch path below).
+    static const bool fused = !(getenv("MAD_LOG_FUSED") && atoi(getenv("MAD_LOG_FUSED")) == 0);
+    if constexpr (YzCfg<R>::ok) if (fused) {
+        using C = YzCfg<R, 32>;
+        const int n_ztiles = (int)mad_ceil_div(nz, C::TZ);
+        const unsigned n_cta = (unsigned)((long long)nx * n_ztiles);
+        // 3 CTAs per SM (168 registers); 2 CTAs with 220 registers and 4 CTAs with 128 registers and a 16-row ring
+        // measured the same 2.3 ms at C2: the kernel is bound by instruction issue, not by latency
+        MAD_CUDA(cudaFuncSetAttribute(log_pass_yz_kernel<R, ACC, 3, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::smem));
+        MAD_PROF("log_pass_yz_kernel", st);
+        log_pass_yz_kernel<R, ACC, 3, 32><<<n_cta, 128, C::smem, st>>>(P0, Q0, log_out, gauss_out, ny, nz, n_ztiles, scale, w);
+        MAD_LAUNCH_OK();
+        return MAD_OK;
+    }
     const long long plane = (long long)ny * nz;
     static const long long slab_env = getenv("MAD_LOG_SLAB") ? atoll(getenv("MAD_LOG_SLAB")) : 0;
     long long slab = slab_env;
