@@ -17,7 +17,8 @@ struct OctDims { int n[2][3]; };
 // scipy _rgi nearest rule: i = clip(floor(p), 0, n-2); idx = (p - i <= .5) ? i : i + 1 -- a half rounds
 // DOWN.  For p in [0, n-1] (guaranteed by the bounds vote) this is exactly ceil(p - 0.5): p - 0.5 is
 // exact for p >= 0.5 and stays in [-0.5, 0) below.
-__device__ __forceinline__ int nearest_idx(double p) { return __double2int_ru(p - 0.5); }
+// ceil without the conversion unit: adding 1.5 * 2^52 with round-up leaves ceil(p - 0.5) in the low word (0 <= p < 2^31).
+__device__ __forceinline__ int nearest_idx(double p) { return __double2loint(__dadd_ru(p - 0.5, 6755399441055744.0)); }
 
 // Exact (reference-arithmetic) classification of one direction: float64 rotation, atan2, acos and
 // the strict-inequality zone test.  Kept out of line: it runs for ~0.1 % of the samples and must
@@ -38,6 +39,9 @@ __device__ __noinline__ int zone_exact_dsc(ZoneTab T, const double* __restrict__
     return 0;                                       // unassigned directions stay in zone 0 (:173)
 }
 
+// SIDE = 2 r known at compile time (16 for the default patch: one lattice column per thread, no tail tests) or 0 for
+// any other radius.
+template <int NB, int SIDE>
 __global__ void __launch_bounds__(256, 3)
 describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1, OctDims dims,
                 const MadKeypoint* __restrict__ kp, const MadOriented* __restrict__ oriented, int r,
@@ -46,7 +50,9 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
     __shared__ int cnt[MAD_DSC_LEN];
     __shared__ ZoneFast F;
     __shared__ int s_bad;
+    __shared__ double xt[32][3];           // lx * Ri[0], lx * Ri[3], lx * Ri[6] for the 2 r values of lx
     const int tid = threadIdx.x;
+    if (SIDE) r = SIDE / 2;
     const MadOriented of = oriented[blockIdx.x];
     const MadKeypoint K = kp[of.kp];
     const int o = K.oct ? 1 : 0;
@@ -57,8 +63,7 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
     float Rmf[9];
 #pragma unroll
     for (int q = 0; q < 9; ++q) { Ri[q] = rf_inv_table[tab + q]; Rmf[q] = (float)rf_table[tab + q]; }
-    const int side = 2 * r;
-    const int total = side * side * side;
+    const int side = SIDE ? SIDE : 2 * r;
     const int c1 = r / 2, c2 = r, c3 = (3 * r) / 2;
     const double cx = K.vox[0], cy = K.vox[1], cz = K.vox[2];
     const double u0 = o ? (-(double)r + 0.5) : (double)(-2 * r + 1);
@@ -67,7 +72,13 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
     for (int q = tid; q < MAD_DSC_LEN; q += blockDim.x) cnt[q] = 0;
     zone_fast_init(&F, T);
     if (tid == 0) s_bad = 0;
+    if (tid < side) {
+        const double lx = u0 + du * tid;
+        xt[tid][0] = lx * Ri[0]; xt[tid][1] = lx * Ri[3]; xt[tid][2] = lx * Ri[6];
+    }
     __syncthreads();
+    float vz_hi[NB];
+    zone_fast_hi<NB>(F, vz_hi);
 
     // Whole-patch bounds vote (RegularGridInterpolator bounds_error, mad/Descriptor.py:140-149).
     // Each coordinate ((lx*a + ly*b) + lz*c) + centre is a monotone function of lx, ly and lz in
@@ -105,17 +116,17 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
         const int by = (j >= c1) + (j >= c2) + (j >= c3);
         const int bz = (k >= c1) + (k >= c2) + (k >= c3);
         const int bin_jk = (16 * by + bz) * T.n_zones;
-        for (int i0 = 0; i0 < side; i0 += GB) {
+#pragma unroll 1                                                  // the unrolled walk (4096 SASS lines) misses the instruction cache
+        for (int i0 = 0; i0 < (SIDE ? SIDE : side); i0 += GB) {
             float4 gv[GB];
 #pragma unroll
             for (int u = 0; u < GB; ++u) {
-                const int i = min(i0 + u, side - 1);
-                const double lx = u0 + du * i;
-                const double px = ((lx * Ri[0] + ay0) + az0) + cx;
-                const double py = ((lx * Ri[3] + ay1) + az1) + cy;
-                const double pz = ((lx * Ri[6] + ay2) + az2) + cz;
+                const int i = SIDE ? i0 + u : min(i0 + u, side - 1);
+                const double px = ((xt[i][0] + ay0) + az0) + cx;
+                const double py = ((xt[i][1] + ay1) + az1) + cy;
+                const double pz = ((xt[i][2] + ay2) + az2) + cz;
                 const int ix = nearest_idx(px), iy = nearest_idx(py), iz = nearest_idx(pz);
-                gv[u] = __ldg(grad + ((long long)ix * ny + iy) * nz + iz);
+                gv[u] = __ldg(grad + (unsigned)((ix * ny + iy) * nz + iz));     // < 2^31 voxels (checked at launch)
             }
             float vx[GB], vy[GB], vz[GB];
             bool valid[GB];
@@ -125,15 +136,15 @@ describe_kernel(const float4* __restrict__ grad0, const float4* __restrict__ gra
                 // squared magnitude with the reference's float32 rounding; m < 1e-5 (zone -1, never counted,
                 // :190) is decided exactly on m2; the fast path normalises with rsqrt (margin-covered)
                 const float m2 = __fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z));
-                valid[u] = (i0 + u < side) && !(m2 < MAD_M2_LT);
-                const float rinv = rsqrtf(fmaxf(m2, 1e-30f));
+                valid[u] = (SIDE || i0 + u < side) && !(m2 < MAD_M2_LT);
+                const float rinv = mad_rsqrt_approx(fmaxf(m2, 1e-30f));
                 vx[u] = ((g.x * Rmf[0] + g.y * Rmf[1]) + g.z * Rmf[2]) * rinv;
                 vy[u] = ((g.x * Rmf[3] + g.y * Rmf[4]) + g.z * Rmf[5]) * rinv;
                 vz[u] = ((g.x * Rmf[6] + g.y * Rmf[7]) + g.z * Rmf[8]) * rinv;
             }
             int zone[GB];
 #pragma unroll
-            for (int u = 0; u < GB; ++u) zone[u] = zone_fast(F, vx[u], vy[u], vz[u]);
+            for (int u = 0; u < GB; ++u) zone[u] = zone_fast<NB>(F, vz_hi, vx[u], vy[u], vz[u]);
 #pragma unroll
             for (int u = 0; u < GB; ++u) {
                 if (valid[u]) {
@@ -171,10 +182,18 @@ extern "C" int mad_describe(const float* grad4_oct0, const float* grad4_oct1, co
     ZoneTab T;
     T.bounds = zones_host->bounds; T.belt_first = zones_host->belt_first; T.belt_phi = zones_host->belt_phi;
     T.n_zones = zones_host->n_zones; T.n_belts = zones_host->n_belts;
+    MAD_CHECK_ARG(T.n_belts >= 1 && T.n_belts <= MAD_BELT_MAX && T.n_zones <= MAD_ZONE_MAX);
     MAD_PROF("describe_kernel", stream);
-    describe_kernel<<<n_oriented, 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, oriented, r,
-        T, rf_table, rf_inv_table, rf_zones, dsc);
+    for (int o = 0; o < 2; ++o)                                  // 32-bit voxel indices in the gather
+        MAD_CHECK_ARG((long long)d.n[o][0] * d.n[o][1] * d.n[o][2] < (1LL << 31));
+    auto launch = [&](auto kernel) {
+        kernel<<<n_oriented, 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, oriented, r,
+            T, rf_table, rf_inv_table, rf_zones, dsc);
+    };
+    if (T.n_belts <= 4 && r == 8) launch(describe_kernel<4, 16>);    // default: 16-zone table (caps + 2 belts), patch 16
+    else if (T.n_belts <= 4) launch(describe_kernel<4, 0>);
+    else launch(describe_kernel<MAD_BELT_MAX, 0>);
     MAD_LAUNCH_OK();
     return MAD_OK;
 }

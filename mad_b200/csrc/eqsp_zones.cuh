@@ -86,54 +86,68 @@ __device__ __forceinline__ float mad_atan2_2pi(float y, float x) {
     return p;
 }
 
+// rsqrt.approx.ftz: one MUFU.RSQ (rsqrtf() adds a denormal-range fix-up branch; the callers clamp the argument to
+// >= 1e-30 and the fast path's guard band covers the 2-ulp error of either form).
+__device__ __forceinline__ float mad_rsqrt_approx(float x) {
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 struct ZoneFast {                    // per-CTA copy in shared memory (zone_fast_init)
-    float tmin[MAD_ZONE_MAX];        // theta bounds shrunk by eps
-    float tmax[MAD_ZONE_MAX];
-    float vz_hi[MAD_BELT_MAX];       // belt b certain iff vz_lo[b] < vz < vz_hi[b]
-    float vz_lo[MAD_BELT_MAX];
-    float t0[MAD_BELT_MAX];          // theta_min of the belt's first zone
-    float k_scale[MAD_BELT_MAX];     // zones / 2 pi
-    int first[MAD_BELT_MAX + 1];
+    float2 tb[MAD_ZONE_MAX];         // theta bounds shrunk by eps: (tmin + eps, tmax - eps)
+    float4 belt[MAD_BELT_MAX];       // x: vz_lo (belt b certain iff vz_lo < vz < vz_hi), y: theta_min of the belt's first
+                                     // zone, z: zones / 2 pi, w: bits = first zone | zones << 16
+    float vz_hi[MAD_BELT_MAX];       // -inf beyond n_belts, so a fixed-length scan counts only real belts
     int n_belts;
 };
 
 __device__ __forceinline__ void zone_fast_init(ZoneFast* F, const ZoneTab& T) {
-    for (int a = threadIdx.x; a < T.n_zones; a += blockDim.x) {
-        F->tmin[a] = (float)(T.bounds[4 * a + 0] + MAD_ZONE_EPS);
-        F->tmax[a] = (float)(T.bounds[4 * a + 2] - MAD_ZONE_EPS);
-    }
-    for (int b = threadIdx.x; b <= T.n_belts; b += blockDim.x) {
-        F->first[b] = T.belt_first[b];
+    for (int a = threadIdx.x; a < T.n_zones; a += blockDim.x)
+        F->tb[a] = make_float2((float)(T.bounds[4 * a + 0] + MAD_ZONE_EPS), (float)(T.bounds[4 * a + 2] - MAD_ZONE_EPS));
+    for (int b = threadIdx.x; b < MAD_BELT_MAX; b += blockDim.x) {
         if (b < T.n_belts) {
             // cos is decreasing on [0, pi]; 1e-6 covers the float32 error of the rotated z component
             F->vz_hi[b] = (float)(cos(T.belt_phi[b] + MAD_ZONE_EPS) - 1e-6);
-            F->vz_lo[b] = (float)(cos(T.belt_phi[b + 1] - MAD_ZONE_EPS) + 1e-6);
-            const int f = T.belt_first[b];
-            F->t0[b] = (float)T.bounds[4 * f + 0];
-            F->k_scale[b] = (float)((double)(T.belt_first[b + 1] - f) / MAD_TWO_PI);
+            const int f = T.belt_first[b], nb = T.belt_first[b + 1] - f;
+            F->belt[b] = make_float4((float)(cos(T.belt_phi[b + 1] - MAD_ZONE_EPS) + 1e-6), (float)T.bounds[4 * f + 0],
+                                     (float)((double)nb / MAD_TWO_PI), __int_as_float(f | (nb << 16)));
+        } else {
+            F->vz_hi[b] = __int_as_float(0xff800000);            // -inf
+            F->belt[b] = make_float4(2.f, 0.f, 0.f, __int_as_float(1 << 16));
         }
     }
     if (threadIdx.x == 0) F->n_belts = T.n_belts;
 }
 
+// Upper vz bounds of the first NB belts, held in registers by the caller for the whole sample loop.
+template <int NB>
+__device__ __forceinline__ void zone_fast_hi(const ZoneFast& F, float (&hi)[NB]) {
+#pragma unroll
+    for (int k = 0; k < NB; ++k) hi[k] = F.vz_hi[k];
+}
+
 // (vx, vy, vz): unit direction in float32.  Returns the zone, or -1 if the exact test must decide.
-// Straight-line code (selects, no branches) so that several independent samples of one thread
-// interleave in the pipeline.
-__device__ __forceinline__ int zone_fast(const ZoneFast& F, float vx, float vy, float vz) {
+// Straight-line code (selects, no branches, no loop: NB >= n_belts is a compile-time bound) so that several
+// independent samples of one thread interleave in the pipeline; two shared-memory loads per sample.
+template <int NB>
+__device__ __forceinline__ int zone_fast(const ZoneFast& F, const float (&hi)[NB], float vx, float vy, float vz) {
     // belts are contiguous and descending in vz: the belt is the number of upper bounds above vz
     int cntb = 0;
-    for (int k = 0; k < F.n_belts; ++k) cntb += (vz < F.vz_hi[k]) ? 1 : 0;
+#pragma unroll
+    for (int k = 0; k < NB; ++k) cntb += (vz < hi[k]) ? 1 : 0;
     const int b = max(cntb - 1, 0);
-    const bool belt_ok = (cntb > 0) && (vz > F.vz_lo[b]);
-    const int first = F.first[b];
-    const int nb = F.first[b + 1] - first;
+    const float4 B = F.belt[b];
+    const bool belt_ok = (cntb > 0) && (vz > B.x);
+    const int fb = __float_as_int(B.w);
+    const int first = fb & 0xFFFF, nb = fb >> 16;
     const float th = mad_atan2_2pi(vy, vx);
-    float u = th - F.t0[b];
+    float u = th - B.y;
     u += (u < 0.f) ? 6.2831855f : 0.f;
-    const int z = first + min((int)(u * F.k_scale[b]), nb - 1);
+    const int z = first + min((int)(u * B.z), nb - 1);
     const float sth = th + 6.2831855f;
-    const float tlo = F.tmin[z], thi = F.tmax[z];
-    const bool in = ((th > tlo) & (th < thi)) | ((sth > tlo) & (sth < thi));
+    const float2 t = F.tb[z];
+    const bool in = ((th > t.x) & (th < t.y)) | ((sth > t.x) & (sth < t.y));
     // a polar cap (one zone in the belt) accepts every theta (theta = 0 passes through theta + 2 pi)
     return (belt_ok && (in || nb == 1)) ? z : -1;
 }

@@ -79,6 +79,7 @@ __device__ __forceinline__ int select_zones(bool flag, int zone, int* out, int* 
     return total;
 }
 
+template <int NB>
 __global__ void __launch_bounds__(128)
 orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1, OctDims dims,
               const MadKeypoint* __restrict__ kp, int r, const char4* __restrict__ mask_off, int n_mask,
@@ -111,6 +112,8 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
     if (tid == 0) { s_hmax = 0; s_count = 0; }
     zone_fast_init(&F, T);
     __syncthreads();
+    float vz_hi[NB];
+    zone_fast_hi<NB>(F, vz_hi);
 
     // ---- step01 + first histogram (float32 angles against float64 bounds) ----
     constexpr int GB = 4;                  // gathers issued per thread before the first one is consumed
@@ -132,10 +135,10 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
             float4 g = gv[u];
             // squared magnitude with NumPy's float32 rounding; the 1e-5 cut-offs are decided exactly on it
             const float m2 = __fadd_rn(__fadd_rn(__fmul_rn(g.x, g.x), __fmul_rn(g.y, g.y)), __fmul_rn(g.z, g.z));
-            const float rinv = rsqrtf(fmaxf(m2, 1e-30f));
+            const float rinv = mad_rsqrt_approx(fmaxf(m2, 1e-30f));
             g.w = (m2 < MAD_M2_LT) ? 0.f : ((m2 >= MAD_M2_GT) ? rinv : -1.f);
             gv[u] = g;
-            zf[u] = (g.w > 0.f) ? zone_fast(F, g.x * rinv, g.y * rinv, g.z * rinv) : -1;
+            zf[u] = (g.w > 0.f) ? zone_fast<NB>(F, vz_hi, g.x * rinv, g.y * rinv, g.z * rinv) : -1;
         }
 #pragma unroll
         for (int u = 0; u < GB; ++u) {
@@ -189,7 +192,7 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
                     const float vx = fmaf(g.z, rf[2], fmaf(g.y, rf[1], g.x * rf[0])) * g.w;
                     const float vy = fmaf(g.z, rf[5], fmaf(g.y, rf[4], g.x * rf[3])) * g.w;
                     const float vz = fmaf(g.z, rf[8], fmaf(g.y, rf[7], g.x * rf[6])) * g.w;
-                    zq[u] = (g.w > 0.f) ? zone_fast(F, vx, vy, vz) : -1;
+                    zq[u] = (g.w > 0.f) ? zone_fast<NB>(F, vz_hi, vx, vy, vz) : -1;
                 }
 #pragma unroll
                 for (int u = 0; u < GB; ++u) {
@@ -298,11 +301,20 @@ extern "C" int mad_orient(const float* grad4_oct0, const float* grad4_oct1, cons
     T.n_zones = zones_host->n_zones; T.n_belts = zones_host->n_belts;
     const size_t smem = (size_t)n_mask * sizeof(float4);
     if (smem > 200 * 1024) { mad_set_error("mad_orient: patch radius %d too large", r); return MAD_ERR_ARG; }
-    MAD_CUDA(cudaFuncSetAttribute(orient_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
-    MAD_PROF("orient_kernel", stream);
-    orient_kernel<<<n_kp, 128, smem, (cudaStream_t)stream>>>(
-        reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, r, mask,
-        n_mask, T, r1_table, lim_main, lim_sec, n_ori, slots);
+    MAD_CHECK_ARG(T.n_belts >= 1 && T.n_belts <= MAD_BELT_MAX && T.n_zones <= MAD_ZONE_MAX);
+    auto launch = [&](auto kernel) -> int {
+        MAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
+        MAD_PROF("orient_kernel", stream);
+        kernel<<<n_kp, 128, smem, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, r, mask,
+            n_mask, T, r1_table, lim_main, lim_sec, n_ori, slots);
+        return MAD_OK;
+    };
+    int lrc;
+    if (T.n_belts <= 4) lrc = launch(orient_kernel<4>);
+    else if (T.n_belts <= 12) lrc = launch(orient_kernel<12>);    // the 112-zone table has 10 belts
+    else lrc = launch(orient_kernel<MAD_BELT_MAX>);
+    if (lrc != MAD_OK) return lrc;
     MAD_LAUNCH_OK();
     return MAD_OK;
 }
