@@ -61,7 +61,14 @@ typedef struct MadZoneTable {
     const double* bounds;     /* [n_zones][4]                                                 */
     const int32_t* belt_first;/* [n_belts+1] first zone index of each belt                    */
     const double* belt_phi;   /* [n_belts+1] phi bounds of the belts                          */
+    const void* fast;         /* device image built once by mad_zone_fast_build (MAD_ZONE_FAST_BYTES), or
+                               * NULL: every CTA then derives it from the table itself                */
 } MadZoneTable;
+
+/* Builds the float32 fast-classification image of a zone table (guard-banded bounds, see csrc/eqsp_zones.cuh)
+ * into fast_out (device, MAD_ZONE_FAST_BYTES); store the pointer in MadZoneTable.fast. */
+#define MAD_ZONE_FAST_BYTES 2048
+int mad_zone_fast_build(const MadZoneTable* zones_host, void* fast_out, void* stream);
 
 const char* mad_last_error_string(void);
 int mad_version(void);

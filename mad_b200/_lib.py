@@ -30,11 +30,12 @@ assert KEYPOINT_DTYPE.itemsize == 48 and ORIENTED_DTYPE.itemsize == 8
 MAX_ORI = 36
 DSC_LEN = 1024
 TOPK_MAX = 32
+ZONE_FAST_BYTES = 2048
 
 
 class MadZoneTable(C.Structure):
     _fields_ = [("n_zones", C.c_int32), ("n_belts", C.c_int32), ("bounds", C.c_void_p),
-                ("belt_first", C.c_void_p), ("belt_phi", C.c_void_p)]
+                ("belt_first", C.c_void_p), ("belt_phi", C.c_void_p), ("fast", C.c_void_p)]
 
 
 class MadDscSet(C.Structure):
@@ -56,6 +57,7 @@ SIGNATURES = {
     "mad_profile_count": (_I, []),
     "mad_profile_get": (_I, [_I, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "mad_profile_reset": (_I, []),
+    "mad_zone_fast_build": (_I, [C.POINTER(MadZoneTable), _P, _P]),
     "mad_grid_max": (_I, [_P, C.c_longlong, _P, _P]),
     "mad_grid_max_decode": (C.c_float, [C.c_uint]),
     "mad_threshold_normalise": (_I, [_P, C.c_longlong, C.c_float, C.c_float, _I, _P]),

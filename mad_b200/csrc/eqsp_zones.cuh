@@ -15,6 +15,7 @@ struct ZoneTab {
     const double* belt_phi;    // [n_belts + 1]
     int n_zones;
     int n_belts;
+    const void* fast;          // prebuilt ZoneFast image (mad_zone_fast_build) or nullptr
 };
 
 #define MAD_TWO_PI 6.283185307179586
@@ -102,7 +103,15 @@ struct ZoneFast {                    // per-CTA copy in shared memory (zone_fast
     int n_belts;
 };
 
+static_assert(sizeof(ZoneFast) <= MAD_ZONE_FAST_BYTES && sizeof(ZoneFast) % 4 == 0, "MAD_ZONE_FAST_BYTES too small");
+
 __device__ __forceinline__ void zone_fast_init(ZoneFast* F, const ZoneTab& T) {
+    if (T.fast) {                                  // prebuilt once per table: a 1.7 KB copy instead of float64 cosines
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(T.fast);
+        uint32_t* dst = reinterpret_cast<uint32_t*>(F);
+        for (int i = threadIdx.x; i < (int)(sizeof(ZoneFast) / 4); i += blockDim.x) dst[i] = __ldg(src + i);
+        return;
+    }
     for (int a = threadIdx.x; a < T.n_zones; a += blockDim.x)
         F->tb[a] = make_float2((float)(T.bounds[4 * a + 0] + MAD_ZONE_EPS), (float)(T.bounds[4 * a + 2] - MAD_ZONE_EPS));
     for (int b = threadIdx.x; b < MAD_BELT_MAX; b += blockDim.x) {

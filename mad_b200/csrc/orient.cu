@@ -298,7 +298,7 @@ extern "C" int mad_orient(const float* grad4_oct0, const float* grad4_oct1, cons
     for (int o = 0; o < 2; ++o) for (int a = 0; a < 3; ++a) d.n[o][a] = dims_oct_host[3 * o + a];
     ZoneTab T;
     T.bounds = zones_host->bounds; T.belt_first = zones_host->belt_first; T.belt_phi = zones_host->belt_phi;
-    T.n_zones = zones_host->n_zones; T.n_belts = zones_host->n_belts;
+    T.n_zones = zones_host->n_zones; T.n_belts = zones_host->n_belts; T.fast = zones_host->fast;
     const size_t smem = (size_t)n_mask * sizeof(float4);
     if (smem > 200 * 1024) { mad_set_error("mad_orient: patch radius %d too large", r); return MAD_ERR_ARG; }
     MAD_CHECK_ARG(T.n_belts >= 1 && T.n_belts <= MAD_BELT_MAX && T.n_zones <= MAD_ZONE_MAX);
@@ -315,6 +315,29 @@ extern "C" int mad_orient(const float* grad4_oct0, const float* grad4_oct1, cons
     else if (T.n_belts <= 12) lrc = launch(orient_kernel<12>);    // the 112-zone table has 10 belts
     else lrc = launch(orient_kernel<MAD_BELT_MAX>);
     if (lrc != MAD_OK) return lrc;
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}
+
+__global__ void zone_fast_build_kernel(ZoneTab T, ZoneFast* out) {
+    __shared__ ZoneFast F;
+    zone_fast_init(&F, T);
+    __syncthreads();
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(&F);
+    uint32_t* dst = reinterpret_cast<uint32_t*>(out);
+    for (int i = threadIdx.x; i < (int)(sizeof(ZoneFast) / 4); i += blockDim.x) dst[i] = src[i];
+}
+
+extern "C" int mad_zone_fast_build(const MadZoneTable* zones_host, void* fast_out, void* stream) {
+    MAD_CHECK_ARG(zones_host && fast_out && zones_host->bounds && zones_host->belt_first && zones_host->belt_phi);
+    MAD_CHECK_ARG(zones_host->n_zones >= 1 && zones_host->n_zones <= MAD_ZONE_MAX);
+    MAD_CHECK_ARG(zones_host->n_belts >= 1 && zones_host->n_belts <= MAD_BELT_MAX);
+    MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(fast_out) & 15) == 0);
+    ZoneTab T;
+    T.bounds = zones_host->bounds; T.belt_first = zones_host->belt_first; T.belt_phi = zones_host->belt_phi;
+    T.n_zones = zones_host->n_zones; T.n_belts = zones_host->n_belts; T.fast = nullptr;
+    MAD_PROF("zone_fast_build_kernel", stream);
+    zone_fast_build_kernel<<<1, 128, 0, (cudaStream_t)stream>>>(T, reinterpret_cast<ZoneFast*>(fast_out));
     MAD_LAUNCH_OK();
     return MAD_OK;
 }

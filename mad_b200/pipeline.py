@@ -81,6 +81,13 @@ class _DeviceTables(object):
         s = _lib.MadZoneTable()
         s.n_zones, s.n_belts = zt.size, zt.n_belts
         s.bounds, s.belt_first, s.belt_phi = b.data_ptr(), f.data_ptr(), p.data_ptr()
+        s.fast = None
+        fast = torch.zeros(_lib.ZONE_FAST_BYTES, dtype=torch.uint8, device=self.device)
+        with torch.cuda.device(self.device):
+            call("mad_zone_fast_build", C.byref(s), _ptr(fast), _stream())
+            torch.cuda.current_stream().synchronize()         # other streams may use the tables right away
+        self.keep.append(fast)
+        s.fast = fast.data_ptr()
         return s
 
 

@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(lib):
 def test_struct_layouts_match_the_header(lib):
     assert lib.KEYPOINT_DTYPE.itemsize == 48          # MadKeypoint
     assert lib.ORIENTED_DTYPE.itemsize == 8           # MadOriented
-    assert C.sizeof(lib.MadZoneTable) == 32
+    assert C.sizeof(lib.MadZoneTable) == 40
     assert C.sizeof(lib.MadDscSet) == 56          # 5 pointers + 3 int32 (+4 padding)
 
 
