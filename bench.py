@@ -264,17 +264,23 @@ def main():
         pairs = P.match_threshold(hi_all, lo, 0.6, impl=args.match_impl)
         return sp, kp, ori, dsc, [pairs]
 
-    def step_e2e():
-        g = grid_pin.to(dev, non_blocking=True)
-        sp, kp, ori, dsc = P.describe_struct(g, exact_f64=exact)
-        # descriptor / keypoint / orientation tables go home on a side stream while matching runs
-        out = [stage.fetch("dsc", dsc, overlap=True), stage.fetch("kp", kp.table[:len(kp)], overlap=True),
-               stage.fetch("ori", ori.table[:len(ori)], overlap=True)]
-        lo = P.DescriptorSet(dsc)
-        ph, pl, sc = P.match_threshold(hi_all, lo, 0.6, impl=args.match_impl)
-        out += [stage.fetch("ph", ph), stage.fetch("pl", pl), stage.fetch("sc", sc)]
-        stage.sync()
-        return out
+    # e2e goes through the streaming API a user of a batch of maps calls (pipeline.MapStream): every step uploads ITS map
+    # from pinned host memory and downloads ITS results (descriptors, keypoints, orientations, pair lists); the upload of
+    # step i+1 and the download of step i-1 overlap the kernels of step i.
+    stream_api = P.MapStream(hi=hi_all, cc=0.6, exact_f64=exact, match_impl=args.match_impl)
+
+    def run_e2e(n_steps):
+        prev, out = None, None
+        nxt = stream_api.upload(grid_pin)
+        for s_i in range(n_steps):
+            cur = nxt
+            nxt = stream_api.upload(grid_pin) if s_i + 1 < n_steps else None
+            ticket = stream_api.submit(cur)
+            if prev is not None:
+                out = stream_api.result(prev)
+            prev = ticket
+        out = stream_api.result(prev)
+        return list(out.values())
 
     def barrier():
         if world > 1:
@@ -314,14 +320,12 @@ def main():
     P.profile_enable(False)
 
     # ---- e2e: host buffers in and out --------------------------------------------------------------
-    for _ in range(2):
-        out = step_e2e()
+    out = run_e2e(2)
     d2h = int(sum(t.numel() * t.element_size() for t in out))
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    for _ in range(args.steps):
-        step_e2e()
+    run_e2e(args.steps)
     e1.record()
     barrier()
     ms_e2e = e0.elapsed_time(e1)

@@ -483,6 +483,77 @@ class HostStage(object):
         if self.copy_stream is not None:
             self.copy_stream.synchronize()
         self.keep = []
+        self.marks = []
+
+    def mark(self):
+        """Records the point after every copy issued so far; ``wait()`` then blocks the host on exactly these copies
+        (and not on later work queued on the compute stream)."""
+        evs = [torch.cuda.Event()]
+        evs[0].record(torch.cuda.current_stream())
+        if self.copy_stream is not None:
+            evs.append(torch.cuda.Event())
+            evs[1].record(self.copy_stream)
+        self.marks = evs
+
+    def wait(self):
+        for ev in getattr(self, "marks", []):
+            ev.synchronize()
+        self.marks = []
+        self.keep = []
+
+
+class MapStream(object):
+    """Streams maps through the hot path (a1-a12, and a15 against resident descriptor sets) with the PCIe copies of
+    neighbouring maps overlapped with the kernels: the upload of the next map runs on a copy stream while the current
+    one is on the SMs, and results travel to pinned host buffers on a side stream while the next map computes.
+
+        ms = MapStream(hi=component_sets, cc=0.6)
+        up = ms.upload(pinned_grid_0)
+        for grid in more_grids:                  # every map: upload -> describe (+ match) -> download
+            nxt = ms.upload(grid); ticket = ms.submit(up); ...; res = ms.result(ticket); up = nxt
+
+    ``result`` returns host arrays: dsc int16 [D][1024], kp / ori tables and, with ``hi``, the pair lists."""
+
+    def __init__(self, hi=None, cc=0.6, exact_f64=True, match_impl=None, patch_size=16, depth=2):
+        _require_cuda()
+        self.hi = _as_set(hi) if hi is not None else None
+        self.cc, self.exact, self.impl, self.patch = cc, exact_f64, match_impl, patch_size
+        self.up_stream = torch.cuda.Stream()
+        self.stages = [HostStage() for _ in range(max(2, depth))]
+        self.n = 0
+
+    def upload(self, grid):
+        """Starts the host -> device copy of a float32 [x][y][z] grid (pinned CPU tensor for an asynchronous copy)."""
+        if isinstance(grid, np.ndarray):
+            grid = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float32))
+        with torch.cuda.stream(self.up_stream):
+            g = grid.to(torch.device("cuda", torch.cuda.current_device()), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.up_stream)
+        return g, ev
+
+    def submit(self, uploaded):
+        g, ev = uploaded
+        cur = torch.cuda.current_stream()
+        cur.wait_event(ev)
+        g.record_stream(cur)
+        stage = self.stages[self.n % len(self.stages)]
+        self.n += 1
+        stage.wait()                                    # the slot's previous results have left the device
+        sp, kp, ori, dsc = describe_struct(g, patch_size=self.patch, exact_f64=self.exact)
+        out = {"dsc": stage.fetch("dsc", dsc, overlap=True), "kp": stage.fetch("kp", kp.table[:len(kp)], overlap=True),
+               "ori": stage.fetch("ori", ori.table[:len(ori)], overlap=True)}
+        if self.hi is not None:
+            ph, pl, sc = match_threshold(self.hi, DescriptorSet(dsc), self.cc, impl=self.impl)
+            out.update(pair_hi=stage.fetch("ph", ph, overlap=True), pair_lo=stage.fetch("pl", pl, overlap=True),
+                       score=stage.fetch("sc", sc, overlap=True))
+        stage.mark()
+        return stage, out
+
+    def result(self, ticket):
+        stage, out = ticket
+        stage.wait()
+        return out
 
 
 def concat_sets(sets):

@@ -392,6 +392,37 @@ def test_host_stage_roundtrip(P):
     assert np.array_equal(a.numpy(), x.cpu().numpy()) and np.array_equal(b.numpy(), x.cpu().numpy() * 0.5)
 
 
+def test_map_stream_equals_separate_calls(P):
+    """MapStream (uploads / downloads of neighbouring maps overlapped with the kernels) returns for every map exactly what
+    describe_struct + match_threshold return for it, whatever the interleaving."""
+    import synth
+    grids = [synth.dequantise_u16(H.golden(n)["input_q"]) for n in ("pair_lo", "pair_hi", "small", "pair_lo")]
+    _, _, _, hi_dsc = P.describe_struct(grids[1])
+    hi = P.DescriptorSet(hi_dsc)
+    want = []
+    for g in grids:
+        sp, kp, ori, dsc = P.describe_struct(g)
+        ph, pl, sc = P.match_threshold(hi, P.DescriptorSet(dsc), 0.6)
+        want.append((dsc.cpu().numpy(), kp.host(), ori.host(), ph.cpu().numpy(), pl.cpu().numpy(), sc.cpu().numpy()))
+    ms = P.MapStream(hi=hi, cc=0.6)
+    pinned = [torch.from_numpy(g).pin_memory() for g in grids]
+    got, prev = [], None
+    nxt = ms.upload(pinned[0])
+    for i in range(len(grids)):
+        cur = nxt
+        nxt = ms.upload(pinned[i + 1]) if i + 1 < len(grids) else None
+        ticket = ms.submit(cur)
+        if prev is not None:
+            got.append({k: v.numpy().copy() for k, v in ms.result(prev).items()})
+        prev = ticket
+    got.append({k: v.numpy().copy() for k, v in ms.result(prev).items()})
+    for w, g in zip(want, got):
+        assert np.array_equal(w[0], g["dsc"])
+        assert w[1].tobytes() == g["kp"].tobytes() and w[2].tobytes() == g["ori"].tobytes()
+        assert np.array_equal(w[3], g["pair_hi"]) and np.array_equal(w[4], g["pair_lo"]) and np.array_equal(w[5], g["score"])
+    assert len(got[0]["pair_hi"]) == len(H.golden("pair_match")["pairs"])
+
+
 def test_c3_size_scale_space_linearity(P):
     """BASELINE config 3 size (512^3 -> 530^3 + 1059^3 grids, ~50 GB of device arrays): the stencil
     chain runs at that size and is exactly linear under power-of-two scaling; detection on the
