@@ -367,6 +367,7 @@ def main():
     VV = V0 + V1
     alg = {
         "log_pass_x_kernel": ("hbm", 12 * VV), "log_pass_y_kernel": ("hbm", 20 * VV), "log_pass_z_kernel": ("hbm", 20 * VV),
+        "log_pass_yz_kernel": ("hbm", 16 * VV),          # fused Y + Z: reads P0, Q0, writes LoG, Gauss
         "gradient_kernel": ("hbm", 16 * VV + 4 * VV), "detect_peaks_kernel": ("hbm", 4 * VV),
         "spline_up_z_kernel": ("hbm", 4 * V1 + 8 * 2 * V1), "spline_up_x_kernel": ("hbm", 8 * 2 * V1 + 8 * 4 * V1),
         "spline_up_y_kernel": ("hbm", 8 * 4 * V1 + 4 * V0), "pad3d_kernel": ("hbm", 4 * n_vox + 4 * V1),
@@ -397,6 +398,15 @@ def main():
         roofline = kernel_roofline(nm)
         if roofline:
             break
+    if roofline and roofline["kernel"] == "log_pass_yz_kernel":
+        # This kernel moves exactly its algorithmic bytes (ncu traffic == 16 B/voxel) but is bound by FP64 issue:
+        # SciPy's float64 line accumulation costs 43 (Y, computed for 128 columns per 112 kept) + 60 (Z) FP64
+        # operations per voxel.  Peak = DFMA / DADD / DMUL issue rate measured on this part
+        # (scripts/ubench/fp64_rate.cu, profiles/r01_fp64_issue_rate.txt: 63 lanes/clk/SM = 18.3 T lane-ops/s).
+        ops = (43.0 * 128.0 / 112.0 + 60.0) * VV
+        t_s = roofline["ms_per_step"] * 1e-3
+        roofline["fp64_issue"] = {"lane_ops_per_voxel": round(ops / VV, 1), "achieved": ops / t_s / 1e12, "peak": 18.3,
+                                  "unit": "T lane-ops/s", "frac": ops / t_s / 1e12 / 18.3}
     per_kernel = {}
     for nm, _, _ in kernels:
         r = kernel_roofline(nm)

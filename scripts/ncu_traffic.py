@@ -6,7 +6,7 @@ import sys
 
 MAP = [("pad3d_kernel", "pad3d_kernel"), ("spline_up_z_kernel", "spline_up_z_kernel"),
        ("spline_up_strided_kernel<double, double", "spline_up_x_kernel"), ("spline_up_strided_kernel<double, float", "spline_up_y_kernel"),
-       ("log_pass_strided_kernel", None), ("log_pass_z_kernel", "log_pass_z_kernel"), ("gradient_kernel", "gradient_kernel"),
+       ("log_pass_strided_kernel", None), ("log_pass_z_kernel", "log_pass_z_kernel"), ("log_pass_yz_kernel", "log_pass_yz_kernel"), ("gradient_kernel", "gradient_kernel"),
        ("detect_peaks_kernel", "detect_peaks_kernel"), ("orient_kernel", "orient_kernel"), ("describe_kernel", "describe_kernel"),
        ("match_u8_kernel", "match_u8_pairs_kernel")]
 rows = list(csv.reader(open(sys.argv[1])))
