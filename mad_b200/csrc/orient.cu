@@ -63,14 +63,15 @@ __device__ __noinline__ void vote_exact_f64(ZoneTab T, const double* __restrict_
 }
 
 // Ordered compaction of the zones [lo, hi) whose flag is set into out[0..8) (ascending zone index, as
-// the reference's np.where); returns the total count.  Called by all 128 threads (4 warps).
+// the reference's np.where); returns the total count.  Called by every thread of the CTA (<= 8 warps).
 __device__ __forceinline__ int select_zones(bool flag, int zone, int* out, int* warp_cnt) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const unsigned m = __ballot_sync(0xFFFFFFFFu, flag);
     if (lane == 0) warp_cnt[warp] = __popc(m);
     __syncthreads();
     int base = 0, total = 0;
-    for (int w = 0; w < 4; ++w) { const int c = warp_cnt[w]; if (w < warp) base += c; total += c; }
+    const int nw = blockDim.x >> 5;
+    for (int w = 0; w < nw; ++w) { const int c = warp_cnt[w]; if (w < warp) base += c; total += c; }
     if (flag) {
         const int p = base + __popc(m & ((1u << lane) - 1u));
         if (p < 8) out[p] = zone;
@@ -90,7 +91,7 @@ orient_kernel(const float4* __restrict__ grad0, const float4* __restrict__ grad1
     __shared__ int hist[128];
     __shared__ int hn0[128];
     __shared__ int cur[128];
-    __shared__ int s_main[8], s_sec[8], s_wcnt[4];
+    __shared__ int s_main[8], s_sec[8], s_wcnt[8];
     __shared__ int s_hmax, s_count;
     __shared__ ZoneFast F;
 
@@ -305,7 +306,8 @@ extern "C" int mad_orient(const float* grad4_oct0, const float* grad4_oct1, cons
     auto launch = [&](auto kernel) -> int {
         MAD_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max<size_t>(smem, 48 * 1024)));
         MAD_PROF("orient_kernel", stream);
-        kernel<<<n_kp, 128, smem, (cudaStream_t)stream>>>(
+        kernel<<<n_kp, 128, smem, (cudaStream_t)stream>>>(      // 64 / 256 threads measured 0.75 / 0.53 ms against 0.50 at C2
+
             reinterpret_cast<const float4*>(grad4_oct0), reinterpret_cast<const float4*>(grad4_oct1), d, kp, r, mask,
             n_mask, T, r1_table, lim_main, lim_sec, n_ori, slots);
         return MAD_OK;
