@@ -340,36 +340,44 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         // the float64 test runs at flush time with the lanes working on 32 candidates in parallel,
         // so its latency (L2 load of the lo norm, DSQRT, DDIV) is not serialised per hit.
         int stg_n = 0;                                               // candidates staged by this warp (warp-uniform register)
+        static_assert(STG == 96, "flush handles three candidates per lane");
         auto flush = [&](int n) {
-            // Pass 1: exact float64 test of 32 staged candidates per round, survivors compacted in
-            // place (a survivor's slot is never above the slot it was read from).  Pass 2: ONE global
-            // atomicAdd reserves the output range, then a coalesced copy.
+            // Exact float64 test of the (<= 96) staged candidates, three per lane with their norm loads issued together
+            // (one L2 latency per flush instead of one per round), survivors compacted in place, then ONE global
+            // atomicAdd reserves the output range and the copy is coalesced.  Staged entries carry (row, col) in the two
+            // halves of a 64-bit word: no division here, the row-major rank row * N + col is formed at copy-out.
             __syncwarp();
-            int total = 0;
-            for (int i0 = 0; i0 < n; i0 += 32) {
-                const int i = i0 + lane;
-                unsigned long long key = 0ull;
-                int dot = 0;
-                bool ok = false;
+            unsigned long long ent[3];
+            int dot[3];
+            double n2r[3], n2c[3];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const int i = lane + 32 * k;
+                ent[k] = 0ull; dot[k] = 0; n2r[k] = -1.0; n2c[k] = 0.0;           // n2r < 0: no candidate / padded hi row
                 if (i < n) {
-                    key = my_key[i];
-                    dot = my_dot[i];
-                    const int r = (int)(key / (unsigned long long)a.N), c = (int)(key % (unsigned long long)a.N);
+                    ent[k] = my_key[i];
+                    dot[k] = my_dot[i];
+                    const int r = (int)(ent[k] >> 32), c = (int)(unsigned)ent[k];
                     if (r < a.M) {
-                        const double s = mad_score(dot, (double)__ldg(a.hi_n2 + r), (double)__ldg(a.lo_n2 + c));
-                        ok = s > a.cc;
+                        n2r[k] = (double)__ldg(a.hi_n2 + r);
+                        n2c[k] = (double)__ldg(a.lo_n2 + c);
                     }
                 }
+            }
+            __syncwarp();                                            // every staged entry is in registers: slots may be rewritten
+            int total = 0;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const bool ok = n2r[k] >= 0.0 && mad_score(dot[k], n2r[k], n2c[k]) > a.cc;         // a zero norm scores 0
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-                __syncwarp();
                 if (ok) {
                     const int p = total + __popc(m & ((1u << lane) - 1u));
-                    my_key[p] = key;
-                    my_dot[p] = dot;
+                    my_key[p] = (ent[k] >> 32) * (unsigned long long)a.N + (ent[k] & 0xFFFFFFFFull);
+                    my_dot[p] = dot[k];
                 }
                 total += __popc(m);
-                __syncwarp();
             }
+            __syncwarp();
             if (total > 0) {
                 unsigned long long gb = 0;
                 if (lane == 0) gb = atomicAdd(a.count, (unsigned long long)total);
@@ -453,47 +461,28 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                         }
                     }
                 } else {
-                    // Pairs: no atomics on the hot path.  The warp's candidates of this chunk get consecutive
-                    // staging slots from a shuffle prefix sum; each lane then writes its own (usually <= 1)
-                    // candidates, reading the dot product out of its registers through the select tree.
+                    // Pairs: no atomics on the hot path; each lane writes its own (usually <= 1) candidates, reading the
+                    // dot product out of its registers through the select tree.
                     const int left = a.N - (n0 + c0);                // columns of this chunk that exist (rnorm is 0 beyond N,
                     if (left < 32) mask &= (left <= 0) ? 0u : ((1u << left) - 1u);   // but cc <= 0 would let padding through)
-                    if (__any_sync(0xFFFFFFFFu, mask != 0u)) {
-                        const int cnt = __popc(mask);
-                        int incl = cnt;
-#pragma unroll
-                        for (int o = 1; o < 32; o <<= 1) {
-                            const int nb = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-                            if (lane >= o) incl += nb;
+                    // One ballot per round hands every lane that still has a candidate its staging slot (round r takes
+                    // the r-th candidate of each lane; most lanes have none, a few one): ~100 cycles of latency per round
+                    // instead of the five dependent shuffles of a prefix sum.  A chunk with a hit sits on the critical path
+                    // of its tile (the accumulator is released when the slowest of the pair's 16 epilogue warps is done).
+                    const unsigned lt = (1u << lane) - 1u;
+                    for (;;) {
+                        const unsigned b = __ballot_sync(0xFFFFFFFFu, mask != 0u);
+                        if (b == 0u) break;
+                        const int nb = __popc(b);
+                        if (stg_n + nb > STG) { flush(stg_n); stg_n = 0; }
+                        if (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const int p = stg_n + __popc(b & lt);
+                            my_key[p] = ((unsigned long long)(unsigned)row << 32) | (unsigned long long)(unsigned)(n0 + c0 + j);
+                            my_dot[p] = (int)mad_select32(v, j);
                         }
-                        const int total = __shfl_sync(0xFFFFFFFFu, incl, 31);
-                        if (stg_n + total > STG) { flush(stg_n); stg_n = 0; }
-                        if (total <= STG) {
-                            int p = stg_n + incl - cnt;
-                            while (mask) {
-                                const int j = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                my_key[p] = (unsigned long long)row * (unsigned long long)a.N + (unsigned long long)(n0 + c0 + j);
-                                my_dot[p] = (int)mad_select32(v, j);
-                                ++p;
-                            }
-                            stg_n += total;
-                        } else {                                     // > STG candidates in one 32 x 32 chunk: exact test right here
-                            while (mask) {
-                                const int j = __ffs(mask) - 1;
-                                mask &= mask - 1;
-                                const int dot = (int)mad_select32(v, j);
-                                const int col = n0 + c0 + j;
-                                const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
-                                if (s > a.cc) {
-                                    const unsigned long long gp = atomicAdd(a.count, 1ULL);
-                                    if (gp < a.cap) {
-                                        a.cand_key[gp] = (unsigned long long)row * (unsigned long long)a.N + (unsigned long long)col;
-                                        a.cand_dot[gp] = dot;
-                                    }
-                                }
-                            }
-                        }
+                        stg_n += nb;
                     }
                 }
             }
