@@ -341,39 +341,43 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         // so its latency (L2 load of the lo norm, DSQRT, DDIV) is not serialised per hit.
         int stg_n = 0;                                               // candidates staged by this warp (warp-uniform register)
         static_assert(STG == 96, "flush handles three candidates per lane");
+        const double cc2 = a.cc * a.cc;
         auto flush = [&](int n) {
-            // Exact float64 test of the (<= 96) staged candidates, three per lane with their norm loads issued together
-            // (one L2 latency per flush instead of one per round), survivors compacted in place, then ONE global
-            // atomicAdd reserves the output range and the copy is coalesced.  Staged entries carry (row, col) in the two
-            // halves of a 64-bit word: no division here, the row-major rank row * N + col is formed at copy-out.
+            // Exact float64 decision for the (<= 96) staged candidates, three per lane, survivors compacted in place, then
+            // ONE global atomicAdd reserves the output range and the copy is coalesced.  A staged entry is self-contained:
+            // |lo|^2 in the high word, (column << 5 | owning lane) in the low word -- |hi|^2 comes from the owning lane by
+            // shuffle, so a flush touches no global memory before its atomic.  The comparison dot / sqrt(p) > cc is decided
+            // on exact integers, dot^2 against cc^2 p, whenever the two differ by more than 1e-13 relative (sqrt and division
+            // are correctly rounded: their 2.3e-16 cannot flip such a case); only closer cases evaluate the quotient itself.
             __syncwarp();
             unsigned long long ent[3];
             int dot[3];
-            double n2r[3], n2c[3];
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
                 const int i = lane + 32 * k;
-                ent[k] = 0ull; dot[k] = 0; n2r[k] = -1.0; n2c[k] = 0.0;           // n2r < 0: no candidate / padded hi row
-                if (i < n) {
-                    ent[k] = my_key[i];
-                    dot[k] = my_dot[i];
-                    const int r = (int)(ent[k] >> 32), c = (int)(unsigned)ent[k];
-                    if (r < a.M) {
-                        n2r[k] = (double)__ldg(a.hi_n2 + r);
-                        n2c[k] = (double)__ldg(a.lo_n2 + c);
-                    }
-                }
+                ent[k] = (i < n) ? my_key[i] : 0ull;
+                dot[k] = (i < n) ? my_dot[i] : 0;
             }
             __syncwarp();                                            // every staged entry is in registers: slots may be rewritten
             int total = 0;
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const bool ok = n2r[k] >= 0.0 && mad_score(dot[k], n2r[k], n2c[k]) > a.cc;         // a zero norm scores 0
+                const unsigned low = (unsigned)ent[k];
+                const int owner = (int)(low & 31u);
+                const double n2r = (double)__shfl_sync(0xFFFFFFFFu, n2a_i, owner);
+                const double n2c = (double)(unsigned)(ent[k] >> 32);
+                bool ok = false;
+                if (lane + 32 * k < n) {
+                    const double p = n2r * n2c, lhs = (double)dot[k] * (double)dot[k], rhs = cc2 * p;
+                    if (p > 0.0 && a.cc > 0.0 && lhs > rhs * (1.0 + 1e-13)) ok = true;
+                    else if (p > 0.0 && a.cc > 0.0 && lhs < rhs * (1.0 - 1e-13)) ok = false;
+                    else ok = mad_score(dot[k], n2r, n2c) > a.cc;     // a zero norm scores 0
+                }
                 const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
                 if (ok) {
-                    const int p = total + __popc(m & ((1u << lane) - 1u));
-                    my_key[p] = (ent[k] >> 32) * (unsigned long long)a.N + (ent[k] & 0xFFFFFFFFull);
-                    my_dot[p] = dot[k];
+                    const int pos = total + __popc(m & ((1u << lane) - 1u));
+                    my_key[pos] = (unsigned long long)(m0 + q * 32 + owner) * (unsigned long long)a.N + (unsigned long long)(low >> 5);
+                    my_dot[pos] = dot[k];
                 }
                 total += __popc(m);
             }
@@ -399,6 +403,15 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             if (gt < BN / 4) {
                 const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.lo_rnorm + (long long)t * TN + c_lo) + gt);
                 reinterpret_cast<float4*>(my_rb + buf * 256)[gt] = r4;
+                if (MODE == MODE_PAIRS) {                            // |lo|^2 (exact integers) in the buffer's unused upper half
+                    const int c = t * TN + c_lo + 4 * gt;
+                    int4 n4;
+                    n4.x = (c < a.N) ? __ldg(a.lo_n2 + c) : 0;
+                    n4.y = (c + 1 < a.N) ? __ldg(a.lo_n2 + c + 1) : 0;
+                    n4.z = (c + 2 < a.N) ? __ldg(a.lo_n2 + c + 2) : 0;
+                    n4.w = (c + 3 < a.N) ? __ldg(a.lo_n2 + c + 3) : 0;
+                    reinterpret_cast<int4*>(my_rb + buf * 256 + 128)[gt] = n4;
+                }
             }
         };
         auto group_sync = [&]() { asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory"); };
@@ -479,7 +492,8 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                             const int j = __ffs(mask) - 1;
                             mask &= mask - 1;
                             const int p = stg_n + __popc(b & lt);
-                            my_key[p] = ((unsigned long long)(unsigned)row << 32) | (unsigned long long)(unsigned)(n0 + c0 + j);
+                            my_key[p] = ((unsigned long long)(unsigned)__float_as_int(rbt[c0 + j + 128]) << 32) |
+                                        (unsigned long long)(((unsigned)(n0 + c0 + j) << 5) | (unsigned)lane);
                             my_dot[p] = (int)mad_select32(v, j);
                         }
                         stg_n += nb;
@@ -639,6 +653,7 @@ int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, i
     const int ncta = pick_ncta(M, N_pad);
     int rc = launch_common(hi_u8, M_pad, lo_u8, N_pad, ncta, &map_hi, &map_lo);
     if (rc != MAD_OK) return rc;
+    if (N_pad > (1 << 27)) { mad_set_error("mad_match_pairs: more than 2^27 lo rows"); return MAD_ERR_ARG; }   // staged entries hold column << 5
     U8Args a = {};
     a.M = M; a.N = N;
     a.S = mad_match_u8_segments(M, N);
