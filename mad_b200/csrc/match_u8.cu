@@ -20,7 +20,7 @@
 //   warps 4..11 epilogue     : two groups of 4 warps alternating tiles; tcgen05.ld (32 lanes x 32
 //                              columns), thread = one hi row
 //        PAIRS mode: hits (row, col, dot) are staged per warp in shared memory and appended to a
-//                    global candidate list with one atomicAdd per flush; a radix sort by
+//                    global candidate list by the drain warps (one atomicAdd per half buffer); a radix sort by
 //                    (row, col) afterwards restores np.where's row-major order (match_finish).
 //        TOPK mode : per-row running top-k in the thread, one partial list per lo segment.
 #include <cuda.h>
@@ -216,7 +216,11 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     auto tempty_bar = [&](int q) { return bars + 8u * (2 * NSTAGE + ACCS + q); };   // (ACCS slots reserved, NACC used)
     const uint32_t a_bar = bars + 8u * (2 * NSTAGE + 2 * ACCS);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(gen + BAR_OFF + 8 * (2 * NSTAGE + 2 * ACCS + 1));
-    int* s_cnt = reinterpret_cast<int*>(gen + BAR_OFF + 8 * (2 * NSTAGE + 2 * ACCS + 2));       // [EPI_WARPS]
+    // hand-off words between the epilogue warps and the two drain warps (PAIRS mode): [EPI_WARPS][2] half-buffer states
+    // (0 = free, n > 0 = n staged entries ready) followed by [EPI_WARPS] "this epilogue warp has finished" flags
+    volatile int* s_half = reinterpret_cast<volatile int*>(gen + BAR_OFF + 8 * (2 * NSTAGE + 2 * ACCS + 2));
+    volatile int* s_done = s_half + 2 * EPI_WARPS;
+    static_assert(8 * (2 * STAGES + 2 * ACCS + 2) + 3 * EPI_WARPS * sizeof(int) <= 512, "misc shared region");
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;    // 0 = leader of the pair
@@ -235,7 +239,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         mbar_init(a_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (threadIdx.x < EPI_WARPS) s_cnt[threadIdx.x] = 0;
+    if (threadIdx.x < 3 * EPI_WARPS) s_half[threadIdx.x] = 0;
     if (NCTA == 2) cluster_sync_all();                             // barriers of both CTAs exist before any remote arrive
     if (warp == 2) {
         if (NCTA == 2) {
@@ -311,6 +315,82 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 if (NCTA == 2) umma_commit_pair(tfull_bar(acc)); else umma_commit(tfull_bar(acc));
             }
         }
+    } else if (warp >= 2 && warp < 4 && MODE == MODE_PAIRS) {
+        // ===================== drain warps (PAIRS): warp 2 serves epilogue group 0, warp 3 group 1 =====================
+        // The epilogue warps only STAGE the candidates that pass the fp32 pre-filter; when a half buffer is full they
+        // publish it here and carry on in the other half.  These two otherwise idle warps take the float64 decision, reserve
+        // the output range (one global atomicAdd per half buffer) and write the pairs.  All of that used to sit in the
+        // epilogue warps, and with the tile's accumulator released only when the slowest of a pair's 16 epilogue warps is
+        // done, every flush (~1500 cycles) delayed the tensor pipe: 0.32 ms of the 1.50 ms C2 launch.
+        // A staged entry is self-contained: |lo|^2 in the high word, (column << 5 | owning lane) in the low word.  The
+        // comparison dot / sqrt(p) > cc is decided on exact integers, dot^2 against cc^2 p, whenever the two differ by more
+        // than 1e-13 relative (sqrt and division are correctly rounded: their 2.3e-16 cannot flip such a case); only closer
+        // cases evaluate the quotient itself.
+        constexpr int HALF = STG / 2;
+        const int e0 = (warp - 2) * 4;                               // first epilogue warp served
+        const double cc2 = a.cc * a.cc;
+        int hi_n2_reg[4];                                            // |hi|^2 of the CTA's 128 rows: lane l holds rows q * 32 + l
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) hi_n2_reg[qq] = (m0 + qq * 32 + lane < a.M) ? __ldg(a.hi_n2 + m0 + qq * 32 + lane) : 0;
+        for (long long spins = 0; spins < (1LL << 27); ++spins) {    // (bounded: a protocol error must not hang the device)
+            int done = 0;
+            for (int e = e0; e < e0 + 4; ++e) done += s_done[e];
+            bool any = false;
+            for (int e = e0; e < e0 + 4; ++e) {
+                for (int h = 0; h < 2; ++h) {
+                    const int n = s_half[2 * e + h];
+                    if (n <= 0) continue;
+                    any = true;
+                    __threadfence_block();                           // the entries were written before the state word
+                    const unsigned long long* hk = stg_key + e * STG + h * HALF;
+                    const int* hd = stg_dot + e * STG + h * HALF;
+                    unsigned long long ent[2];
+                    int dot[2];
+                    bool ok[2];
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        const int i = lane + 32 * k;
+                        ent[k] = (i < n) ? hk[i] : 0ull;
+                        dot[k] = (i < n) ? hd[i] : 0;
+                    }
+                    __syncwarp();
+                    if (lane == 0) s_half[2 * e + h] = 0;            // the half may be refilled: its entries are in registers
+                    int total = 0, pos[2];
+                    const int qe = e & 3;
+                    const int n2_q = qe == 0 ? hi_n2_reg[0] : (qe == 1 ? hi_n2_reg[1] : (qe == 2 ? hi_n2_reg[2] : hi_n2_reg[3]));
+#pragma unroll
+                    for (int k = 0; k < 2; ++k) {
+                        ok[k] = false;
+                        const unsigned low = (unsigned)ent[k];
+                        const double n2r = (double)__shfl_sync(0xFFFFFFFFu, n2_q, (int)(low & 31u));
+                        if (lane + 32 * k < n) {
+                            const int row = m0 + qe * 32 + (int)(low & 31u);
+                            const double n2c = (double)(unsigned)(ent[k] >> 32);
+                            const double p = n2r * n2c, lhs = (double)dot[k] * (double)dot[k], rhs = cc2 * p;
+                            if (p > 0.0 && a.cc > 0.0 && lhs > rhs * (1.0 + 1e-13)) ok[k] = true;
+                            else if (p > 0.0 && a.cc > 0.0 && lhs < rhs * (1.0 - 1e-13)) ok[k] = false;
+                            else ok[k] = mad_score(dot[k], n2r, n2c) > a.cc;     // a zero norm scores 0
+                            ent[k] = (unsigned long long)row * (unsigned long long)a.N + (unsigned long long)(low >> 5);
+                        }
+                        const unsigned m = __ballot_sync(0xFFFFFFFFu, ok[k]);
+                        pos[k] = total + __popc(m & ((1u << lane) - 1u));
+                        total += __popc(m);
+                    }
+                    if (total > 0) {
+                        unsigned long long gb = 0;
+                        if (lane == 0) gb = atomicAdd(a.count, (unsigned long long)total);
+                        gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
+#pragma unroll
+                        for (int k = 0; k < 2; ++k)
+                            if (ok[k] && gb + pos[k] < a.cap) { a.cand_key[gb + pos[k]] = ent[k]; a.cand_dot[gb + pos[k]] = dot[k]; }
+                    }
+                }
+            }
+            if (!any) {
+                if (done == 4) break;                                // flags read BEFORE the scan that found nothing
+                __nanosleep(200);
+            }
+        }
     } else if (warp >= 4) {
         // ===================== epilogue: thread = one hi row =====================
         const int q = warp & 3;                                      // TMEM lane quadrant of this warp
@@ -325,7 +405,6 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         const float thr_pairs = (row_ok && n2a_i > 0) ? ((float)a.cc - 4e-6f) / ra : INFINITY;
         unsigned long long* my_key = stg_key + ew * STG;
         int* my_dot = stg_dot + ew * STG;
-        volatile int* my_cnt = s_cnt + ew;
         constexpr bool kTop = (MODE == MODE_TOPK || MODE == MODE_TOP8);
         constexpr int kList = (MODE == MODE_TOPK) ? MAD_TOPK_MAX : (MODE == MODE_TOP8 ? 8 : 1);
         double bs[kList];
@@ -336,60 +415,24 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             for (int i = 0; i < kList; ++i) { bs[i] = -INFINITY; bi[i] = -1; }
         }
         const int k_last = (MODE == MODE_TOP8) ? 7 : a.k - 1;        // TOP8 keeps 8 entries whatever k <= 8 is
-        // Candidates that pass the fp32 pre-filter are only STAGED here (two shared-memory stores);
-        // the float64 test runs at flush time with the lanes working on 32 candidates in parallel,
-        // so its latency (L2 load of the lo norm, DSQRT, DDIV) is not serialised per hit.
+        // Candidates that pass the fp32 pre-filter are only STAGED here (two shared-memory stores); the drain warps take
+        // the float64 decision and write the pairs.
         int stg_n = 0;                                               // candidates staged by this warp (warp-uniform register)
-        static_assert(STG == 96, "flush handles three candidates per lane");
-        const double cc2 = a.cc * a.cc;
-        auto flush = [&](int n) {
-            // Exact float64 decision for the (<= 96) staged candidates, three per lane, survivors compacted in place, then
-            // ONE global atomicAdd reserves the output range and the copy is coalesced.  A staged entry is self-contained:
-            // |lo|^2 in the high word, (column << 5 | owning lane) in the low word -- |hi|^2 comes from the owning lane by
-            // shuffle, so a flush touches no global memory before its atomic.  The comparison dot / sqrt(p) > cc is decided
-            // on exact integers, dot^2 against cc^2 p, whenever the two differ by more than 1e-13 relative (sqrt and division
-            // are correctly rounded: their 2.3e-16 cannot flip such a case); only closer cases evaluate the quotient itself.
+        constexpr int HALF = STG / 2;
+        static_assert(HALF >= 32, "a half buffer must take one ballot round");
+        int cur = 0;                                                 // half being filled
+        auto publish = [&](int n) {                                  // hand the current half (n entries) to the drain warp
             __syncwarp();
-            unsigned long long ent[3];
-            int dot[3];
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const int i = lane + 32 * k;
-                ent[k] = (i < n) ? my_key[i] : 0ull;
-                dot[k] = (i < n) ? my_dot[i] : 0;
-            }
-            __syncwarp();                                            // every staged entry is in registers: slots may be rewritten
-            int total = 0;
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const unsigned low = (unsigned)ent[k];
-                const int owner = (int)(low & 31u);
-                const double n2r = (double)__shfl_sync(0xFFFFFFFFu, n2a_i, owner);
-                const double n2c = (double)(unsigned)(ent[k] >> 32);
-                bool ok = false;
-                if (lane + 32 * k < n) {
-                    const double p = n2r * n2c, lhs = (double)dot[k] * (double)dot[k], rhs = cc2 * p;
-                    if (p > 0.0 && a.cc > 0.0 && lhs > rhs * (1.0 + 1e-13)) ok = true;
-                    else if (p > 0.0 && a.cc > 0.0 && lhs < rhs * (1.0 - 1e-13)) ok = false;
-                    else ok = mad_score(dot[k], n2r, n2c) > a.cc;     // a zero norm scores 0
+            if (n > 0) {
+                if (lane == 0) {
+                    __threadfence_block();
+                    s_half[2 * ew + cur] = n;
+                    long long spins = 0;
+                    while (s_half[2 * ew + (cur ^ 1)] != 0 && ++spins < (1LL << 27)) __nanosleep(100);   // other half still in use
                 }
-                const unsigned m = __ballot_sync(0xFFFFFFFFu, ok);
-                if (ok) {
-                    const int pos = total + __popc(m & ((1u << lane) - 1u));
-                    my_key[pos] = (unsigned long long)(m0 + q * 32 + owner) * (unsigned long long)a.N + (unsigned long long)(low >> 5);
-                    my_dot[pos] = dot[k];
-                }
-                total += __popc(m);
+                cur ^= 1;
+                __syncwarp();
             }
-            __syncwarp();
-            if (total > 0) {
-                unsigned long long gb = 0;
-                if (lane == 0) gb = atomicAdd(a.count, (unsigned long long)total);
-                gb = __shfl_sync(0xFFFFFFFFu, gb, 0);
-                for (int i = lane; i < total; i += 32)
-                    if (gb + i < a.cap) { a.cand_key[gb + i] = my_key[i]; a.cand_dot[gb + i] = my_dot[i]; }
-            }
-            __syncwarp();
         };
         // Work split between the two epilogue groups.  One-CTA kernel (128-wide tiles, 4 accumulators): the
         // groups alternate tiles.  Pair kernel (256-wide tiles, only 2 accumulators fit TMEM): both groups
@@ -487,11 +530,11 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                         const unsigned b = __ballot_sync(0xFFFFFFFFu, mask != 0u);
                         if (b == 0u) break;
                         const int nb = __popc(b);
-                        if (stg_n + nb > STG) { flush(stg_n); stg_n = 0; }
+                        if (stg_n + nb > HALF) { publish(stg_n); stg_n = 0; }
                         if (mask) {
                             const int j = __ffs(mask) - 1;
                             mask &= mask - 1;
-                            const int p = stg_n + __popc(b & lt);
+                            const int p = cur * HALF + stg_n + __popc(b & lt);
                             my_key[p] = ((unsigned long long)(unsigned)__float_as_int(rbt[c0 + j + 128]) << 32) |
                                         (unsigned long long)(((unsigned)(n0 + c0 + j) << 5) | (unsigned)lane);
                             my_dot[p] = (int)mad_select32(v, j);
@@ -506,7 +549,11 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 if (NCTA == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
             }
         }
-        if (!kTop) flush(stg_n);
+        if (!kTop) {
+            publish(stg_n);
+            __syncwarp();
+            if (lane == 0) { __threadfence_block(); s_done[ew] = 1; }
+        }
         if (kTop && row_ok) {
             // one partial list per (segment, epilogue group): the host merges 2 S lists
             const long long o = ((long long)(seg * 2 + grp) * a.M + row) * a.k;
