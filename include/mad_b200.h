@@ -75,6 +75,12 @@ int mad_version(void);
 /* Fills (sm_count, cc_major, cc_minor) of the current device. */
 int mad_device_info(int* sm_count, int* cc_major, int* cc_minor);
 
+/* Copies `bytes` (a multiple of 4, <= 4096) from device memory to PINNED host memory by a kernel writing over PCIe,
+ * not by a copy engine: a small count does not queue behind a large transfer in flight.  dst_host_mapped: the
+ * device-visible address of the pinned buffer (equal to the host address under unified addressing).  The host reads
+ * the buffer after synchronising the stream or an event recorded behind this call. */
+int mad_publish_small(const void* src_dev, void* dst_host_mapped, int bytes, void* stream);
+
 /* ---- launch accounting and per-kernel timing (no reference counterpart; measurement only) ---- */
 /* Number of kernels this library has launched in this process (CUB-internal kernels count as one
  * per CUB call). */

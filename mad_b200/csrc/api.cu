@@ -212,3 +212,24 @@ extern "C" int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, i
     if (rc != MAD_OK) return rc;
     return mad_topk_merge_launch(pidx, pscore, S, M, k, topk_idx, topk_score, st);
 }
+
+// ---- small device -> host readbacks that do not use a copy engine -------------------------------------------------
+// A cudaMemcpyAsync of a few bytes queues behind whatever large transfer the copy engine of that direction is busy with
+// (observed: a 4-byte count waited 1.5 ms for the 82 MB descriptor table of the previous map).  This kernel stores the
+// words straight into pinned, device-mapped host memory over PCIe instead.
+namespace {
+__global__ void publish_small_kernel(const unsigned int* __restrict__ src, volatile unsigned int* dst, int n_words) {
+    for (int i = threadIdx.x; i < n_words; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+}  // namespace
+
+extern "C" int mad_publish_small(const void* src_dev, void* dst_host_mapped, int bytes, void* stream) {
+    MAD_CHECK_ARG(src_dev && dst_host_mapped && bytes > 0 && bytes <= 4096 && bytes % 4 == 0);
+    MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(src_dev) & 3) == 0 && (reinterpret_cast<uintptr_t>(dst_host_mapped) & 3) == 0);
+    MAD_PROF("publish_small_kernel", stream);
+    publish_small_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(static_cast<const unsigned int*>(src_dev),
+                                                             static_cast<volatile unsigned int*>(dst_host_mapped), bytes / 4);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}

@@ -55,6 +55,37 @@ def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
 
 
+class _Readback(object):
+    """Small device -> host reads (counts) through pinned mapped memory written by a kernel (mad_publish_small): a
+    cudaMemcpy of 4 bytes would queue behind any large transfer the device -> host copy engine is busy with."""
+    _slots = {}
+
+    @classmethod
+    def read(cls, *tensors):
+        """Values of the given small int32 / int64 device tensors as Python ints (one synchronisation)."""
+        dev = tensors[0].device
+        key = (dev.index, torch.cuda.current_stream().cuda_stream)
+        slot = cls._slots.get(key)
+        if slot is None:
+            slot = cls._slots[key] = torch.zeros(512, dtype=torch.int64).pin_memory()
+        st = _stream()
+        off, views = 0, []
+        for t in tensors:
+            t = t.contiguous().view(-1)
+            nbytes = t.numel() * t.element_size()
+            assert nbytes % 4 == 0 and off + nbytes <= slot.numel() * 8
+            call("mad_publish_small", _ptr(t), C.c_void_p(slot.data_ptr() + off), nbytes, st)
+            views.append((off, t.dtype, t.numel()))
+            off += (nbytes + 7) // 8 * 8
+        torch.cuda.current_stream().synchronize()
+        raw = slot.numpy()
+        out = []
+        for o, dt, n in views:
+            a = raw.view(np.uint8)[o:o + n * (8 if dt == torch.int64 else 4)].view(np.int64 if dt == torch.int64 else np.int32)
+            out.extend(int(v) for v in a)
+        return out
+
+
 def _dptr(a):
     return a.ctypes.data_as(C.c_void_p)
 
@@ -208,7 +239,7 @@ def detect(space, border=12, threshold=5e-2, cap=None):
         for o, (lg, (gx, gy, gz)) in enumerate(zip(space.logs, space.dims)):
             call("mad_detect", _ptr(lg), gx, gy, gz, o, int(border), C.c_float(threshold), _ptr(cand), cap,
                  _ptr(counter), st)
-        n = int(counter.item())
+        n = _Readback.read(counter)[0]
         if n <= cap:
             break
         cap = int(n * 1.25) + 16        # rare: candidate list overflowed, redo with room
@@ -218,7 +249,7 @@ def detect(space, border=12, threshold=5e-2, cap=None):
     ws = torch.empty(max(ws_bytes, 1), dtype=torch.uint8, device=dev)
     dims = space.dims_host
     call("mad_sort_keypoints", _ptr(cand), n, _dptr(dims), _ptr(out), _ptr(out_count), _ptr(ws), ws_bytes, st)
-    return Keypoints(out, out_count.item())
+    return Keypoints(out, _Readback.read(out_count)[0])
 
 
 class Oriented(object):
@@ -264,7 +295,7 @@ def orient(space, kp, radius=8, lim_main=6, lim_sec=6):
     ws_bytes = _lib.lib.mad_compact_oriented_workspace_bytes(n)
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     call("mad_compact_oriented", _ptr(n_ori), _ptr(slots), n, _ptr(out), cap, _ptr(out_count), _ptr(ws), ws_bytes, st)
-    return Oriented(out, out_count.item())
+    return Oriented(out, _Readback.read(out_count)[0])
 
 
 def describe(space, kp, ori, radius=8):
@@ -413,7 +444,7 @@ def match_threshold(hi, lo, cc=0.6, impl=None):
 
 def _read_counts(count, hi, lo):
     """One device->host read: (pairs found, largest entry of hi, of lo); caches the maxima."""
-    vals = torch.cat([count.view(-1), hi._max_dev.to(torch.int64), lo._max_dev.to(torch.int64)]).tolist()
+    vals = _Readback.read(count, hi._max_dev, lo._max_dev)
     hi._max_entry, lo._max_entry = int(vals[1]), int(vals[2])
     hi.c.max_entry, lo.c.max_entry = hi._max_entry, lo._max_entry
     return int(vals[0])
