@@ -739,14 +739,25 @@ log_pass_yz_kernel(const float* __restrict__ P0, const float* __restrict__ Q0, f
     const int q_end = ny + 2 * R;                                // samples q = y + R in [0, q_end)
     float* my = ring + tid;
     auto issue = [&](int grp) {
+        const int q0 = grp * T;
+        float* dst0 = my + ((q0 & (D - 1)) * 2) * 128;           // T divides D: the group's slots are consecutive
+        if (q0 >= R && q0 + T <= ny + R) {                       // interior rows: no reflection, one address per group
+            const float* p0 = P0 + base + (long long)(q0 - R) * nz;
+            const float* p1 = Q0 + base + (long long)(q0 - R) * nz;
 #pragma unroll
-        for (int i = 0; i < T; ++i) {
-            const int q = grp * T + i;
-            if (q < q_end) {
-                const long long off = base + (long long)mad_reflect(q - R, ny) * nz;
-                float* dst = my + ((q & (D - 1)) * 2) * 128;
-                cp_async4(dst, P0 + off);
-                cp_async4(dst + 128, Q0 + off);
+            for (int i = 0; i < T; ++i) {
+                cp_async4(dst0 + i * 256, p0 + (long long)i * nz);
+                cp_async4(dst0 + i * 256 + 128, p1 + (long long)i * nz);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                const int q = q0 + i;
+                if (q < q_end) {
+                    const long long off = base + (long long)mad_reflect(q - R, ny) * nz;
+                    cp_async4(dst0 + i * 256, P0 + off);
+                    cp_async4(dst0 + i * 256 + 128, Q0 + off);
+                }
             }
         }
         cp_async_commit();
@@ -820,13 +831,16 @@ log_pass_yz_kernel(const float* __restrict__ P0, const float* __restrict__ Q0, f
         }
         __syncthreads();
         // ---- phase C: coalesced row segments
-        const int ncol = min(TZ, nz - z0);
-        for (int i = tid; i < rows * TZ; i += 128) {
-            const int r = i / TZ, c = i - r * TZ;
-            if (c < ncol) {
-                const long long off = plane + (long long)(a + r) * nz + z0 + c;
-                log_out[off] = sout[(0 * T + r) * OS + c + (c >> 3)];
-                gauss_out[off] = sout[(1 * T + r) * OS + c + (c >> 3)];
+        if (tid < TZ && z0 + tid < nz) {                          // thread = column: every row is one coalesced segment
+            const float* so = sout + tid + (tid >> 3);
+            float* lo_p = log_out + plane + (long long)a * nz + z0 + tid;
+            float* ga_p = gauss_out + plane + (long long)a * nz + z0 + tid;
+#pragma unroll
+            for (int r = 0; r < T; ++r) {
+                if (r < rows) {
+                    lo_p[(long long)r * nz] = so[(0 * T + r) * OS];
+                    ga_p[(long long)r * nz] = so[(1 * T + r) * OS];
+                }
             }
         }
         // the next iteration's first barrier orders these reads of sout before its phase-B writes, and this
