@@ -81,6 +81,11 @@ int mad_device_info(int* sm_count, int* cc_major, int* cc_minor);
  * the buffer after synchronising the stream or an event recorded behind this call. */
 int mad_publish_small(const void* src_dev, void* dst_host_mapped, int bytes, void* stream);
 
+/* Copies `bytes` from device memory to PINNED, device-mapped host memory with n_ctas CTAs storing over PCIe (no copy
+ * engine involved, so nothing else queues behind a large download).  Both addresses 16-byte aligned.  The host reads the
+ * buffer after synchronising the stream or an event recorded behind this call. */
+int mad_copy_to_host(const void* src_dev, void* dst_host_mapped, long long bytes, int n_ctas, void* stream);
+
 /* ---- launch accounting and per-kernel timing (no reference counterpart; measurement only) ---- */
 /* Number of kernels this library has launched in this process (CUB-internal kernels count as one
  * per CUB call). */

@@ -58,6 +58,7 @@ SIGNATURES = {
     "mad_profile_get": (_I, [_I, C.POINTER(C.c_char_p), C.POINTER(C.c_float)]),
     "mad_profile_reset": (_I, []),
     "mad_publish_small": (_I, [_P, _P, _I, _P]),
+    "mad_copy_to_host": (_I, [_P, _P, C.c_longlong, _I, _P]),
     "mad_zone_fast_build": (_I, [C.POINTER(MadZoneTable), _P, _P]),
     "mad_grid_max": (_I, [_P, C.c_longlong, _P, _P]),
     "mad_grid_max_decode": (C.c_float, [C.c_uint]),

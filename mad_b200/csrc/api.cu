@@ -233,3 +233,36 @@ extern "C" int mad_publish_small(const void* src_dev, void* dst_host_mapped, int
     MAD_LAUNCH_OK();
     return MAD_OK;
 }
+
+// ---- bulk device -> host copy by a kernel ---------------------------------------------------------------------------
+// Results of map i travel home while map i+1 is computing.  A cudaMemcpyAsync would keep the device -> host copy engine
+// busy for milliseconds, and every small operation of the next map that the driver routes through a copy engine (the
+// cudaMemsetAsync calls inside CUB's radix sort, for one) queues behind it: the pipelined end-to-end time swung between
+// 9.1 and 14 ms per map depending on how the two happened to align.  A handful of CTAs storing 16-byte words straight into
+// pinned, device-mapped host memory move the same bytes over PCIe without touching a copy engine.
+namespace {
+__global__ void __launch_bounds__(256)
+copy_to_host_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, long long n16, const unsigned char* __restrict__ src_tail,
+                    unsigned char* __restrict__ dst_tail, int n_tail) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n16; i += stride) {
+        const uint4 v = __ldcs(src + i);
+        __stcs(dst + i, v);
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < n_tail) dst_tail[threadIdx.x] = src_tail[threadIdx.x];
+}
+}  // namespace
+
+extern "C" int mad_copy_to_host(const void* src_dev, void* dst_host_mapped, long long bytes, int n_ctas, void* stream) {
+    MAD_CHECK_ARG(src_dev && dst_host_mapped && bytes > 0 && n_ctas >= 1 && n_ctas <= 1024);
+    MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(src_dev) & 15) == 0 && (reinterpret_cast<uintptr_t>(dst_host_mapped) & 15) == 0);
+    const long long n16 = bytes / 16;
+    const int n_tail = (int)(bytes - n16 * 16);
+    const unsigned char* s8 = static_cast<const unsigned char*>(src_dev);
+    unsigned char* d8 = static_cast<unsigned char*>(dst_host_mapped);
+    MAD_PROF("copy_to_host_kernel", stream);
+    copy_to_host_kernel<<<n_ctas, 256, 0, (cudaStream_t)stream>>>(static_cast<const uint4*>(src_dev), static_cast<uint4*>(dst_host_mapped),
+                                                                  n16, s8 + n16 * 16, d8 + n16 * 16, n_tail);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}

@@ -11,6 +11,7 @@ The reference-shaped classes (MapSpace, Detector, Orientator, Descriptor) are th
 these functions.  Nothing here computes on the CPU: without a CUDA device every call raises.
 """
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -477,6 +478,9 @@ def _match_threshold_onepass(hi, lo, cc, dev, st, verify=False):
     return pair_hi[:p], pair_lo[:p], score[:p]
 
 
+HOST_COPY_CTAS = int(os.environ.get("MAD_HOST_COPY_CTAS", "8"))    # 2: copy-bound (12.5 ms per C2 map); 4-8: 9.1-9.6; 16-32: 9.4-9.7
+
+
 class HostStage(object):
     """Pinned host staging buffers for device -> host results, reused across calls: ``fetch`` starts
     an asynchronous copy on the current stream and returns the CPU view, valid after ``sync()``."""
@@ -501,8 +505,14 @@ class HostStage(object):
             if self.copy_stream is None:
                 self.copy_stream = torch.cuda.Stream()
             self.copy_stream.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(self.copy_stream):
-                view.copy_(t, non_blocking=True)
+            t = t.contiguous()
+            if t.data_ptr() % 16 == 0:
+                # a few CTAs store straight into the pinned (device-mapped) buffer: the copy engine stays free, so nothing
+                # of the next map (CUB's internal memsets, ...) queues behind a multi-millisecond download
+                call("mad_copy_to_host", _ptr(t), C.c_void_p(buf.data_ptr()), n, HOST_COPY_CTAS, C.c_void_p(self.copy_stream.cuda_stream))
+            else:
+                with torch.cuda.stream(self.copy_stream):
+                    view.copy_(t, non_blocking=True)
             t.record_stream(self.copy_stream)
             self.keep.append(t)
         else:
