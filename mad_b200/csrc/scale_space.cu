@@ -691,31 +691,27 @@ log_pass_z_kernel(const float* __restrict__ P01, const float* __restrict__ Rr, c
 // halo on either side (reflected at the grid ends): 128 threads, thread t <-> column z0 - R + t.
 //   phase A  every thread marches along y exactly like pass Y above (private cp.async ring, float64 register
 //            windows) and produces T = 8 rows of P01, R, S for its column, rounded to float32 as SciPy stores them
-//            and parked as float64 in a shared-memory stage [3][T][128]; column c of row t sits at
-//            (c & ~7) | ((c & 7) ^ ((7 t + (c >> 4)) & 7)): with u = 14 t + (c >> 3) the 64-bit bank is a bijection of
-//            u mod 16, so the 16 lanes of a half-warp hit 16 different banks both in the column-wise phase-A stores
-//            and in the chunk-strided phase-B window loads;
-//   phase B  T * TZ / 8 work items (row, chunk of 8 z): window of 8 + 2R staged values per array -> Gaussian and the
-//            three Laplacian terms, summed and clamped in float32, written to an output stage;
+//            and parked as float64 in a shared-memory stage [3][T][128];
+//   phase B  128 work items (row, chunk of CW = 7 z) -- every thread has one: window of CW + 2R staged values per array
+//            -> Gaussian and the three Laplacian terms, summed and clamped in float32, written to an output stage;
 //   phase C  the T x TZ output tile goes to HBM as whole row segments (coalesced).
 // Two barriers per T rows; the HBM latency is covered by the cp.async ring as before.
 template <int R, int DEPTH = 32>
 struct YzCfg {
     static constexpr int T = 8, W = T + 2 * R, D = DEPTH, PF = D / T - 1, G0 = 2 * R / T;
     static constexpr int TZ = 128 - 2 * R;                      // output columns per CTA
-    static constexpr int CH = TZ / 8;                           // chunks of 8 columns
-    static constexpr int RS = 128;                              // stage row stride in doubles (XOR-swizzled columns)
-    static constexpr int OS = TZ + TZ / 8;                      // output-stage row stride in floats (one pad per chunk)
+    static constexpr int CH = 128 / T;                          // phase-B chunks per row: T rows x CH chunks = 128 items
+    static constexpr int CW = TZ / CH;                          // columns per chunk (7 for R = 8: odd, see below)
+    static constexpr int RS = 128;                              // stage row stride in doubles
+    static constexpr int OS = TZ;                               // output-stage row stride in floats
     static constexpr size_t ring_bytes = (size_t)D * 2 * 128 * sizeof(float);
     static constexpr size_t stage_bytes = (size_t)3 * T * RS * sizeof(double);
     static constexpr size_t out_bytes = (size_t)2 * T * OS * sizeof(float);
     static constexpr size_t smem = ring_bytes + stage_bytes + out_bytes;
-    static constexpr bool ok = TZ % 8 == 0 && (2 * R) % T == 0 && G0 <= PF + 1;   // R = 4, 8, 12
+    // R = 8 (the LoG of sigma = 2): 112 columns = 16 chunks of 7.  An odd chunk width makes the chunk-strided window loads
+    // of a half-warp (16 items of one row) and the output-stage stores of a warp hit distinct banks with a plain layout.
+    static constexpr bool ok = TZ % CH == 0 && (CW % 2) == 1 && (2 * R) % T == 0 && G0 <= PF + 1;
 };
-
-__device__ __forceinline__ int yz_slot(int row, int col) {
-    return (col & ~7) | ((col & 7) ^ ((7 * row + (col >> 4)) & 7));
-}
 
 template <int R, typename ACC, int MINB, int DEPTH>
 __global__ void __launch_bounds__(128, MINB)
@@ -723,7 +719,8 @@ log_pass_yz_kernel(const float* __restrict__ P0, const float* __restrict__ Q0, f
                    float* __restrict__ gauss_out, int ny, int nz, int n_ztiles, float scale, ConvW w) {
     using C = YzCfg<R, DEPTH>;
     static_assert(C::ok, "the fused pass needs a kernel radius that is a multiple of 4");
-    constexpr int T = C::T, W = C::W, D = C::D, PF = C::PF, G0 = C::G0, TZ = C::TZ, CH = C::CH, RS = C::RS, OS = C::OS;
+    constexpr int T = C::T, W = C::W, D = C::D, PF = C::PF, G0 = C::G0, TZ = C::TZ, CH = C::CH, CW = C::CW, RS = C::RS, OS = C::OS;
+    constexpr int WB = CW + 2 * R;                               // phase-B window
     extern __shared__ __align__(16) unsigned char yz_smem[];
     float* ring = reinterpret_cast<float*>(yz_smem);                                    // [D][2][128]
     double* stage = reinterpret_cast<double*>(yz_smem + C::ring_bytes);                 // [3][T][RS]
@@ -774,7 +771,7 @@ log_pass_yz_kernel(const float* __restrict__ P0, const float* __restrict__ Q0, f
 #pragma unroll
     for (int grp = PF + 1; grp <= PF + G0; ++grp) issue(grp);
     const int br = tid / CH, bc = tid - br * CH;                 // phase-B work item: row br, chunk bc
-    const bool b_active = tid < T * CH && (z0 + bc * 8) < nz;
+    const bool b_active = (z0 + bc * CW) < nz;
     int grp = G0;
     for (int a = 0; a < ny; a += T, ++grp) {
         // ---- phase A: T rows of P01 / R / S for this column
@@ -792,7 +789,7 @@ log_pass_yz_kernel(const float* __restrict__ P0, const float* __restrict__ Q0, f
             conv_g_rows<R, T, ACC>(wb, w, r1);
 #pragma unroll
             for (int t = 0; t < T; ++t) {
-                const int slot = t * RS + yz_slot(t, tid);
+                const int slot = t * RS + tid;
                 stage[0 * T * RS + slot] = (double)r0[t];        // P01 (float32-rounded as SciPy stores it)
                 stage[1 * T * RS + slot] = (double)r2[t];        // R
                 stage[2 * T * RS + slot] = (double)r1[t];        // S
@@ -807,32 +804,32 @@ log_pass_yz_kernel(const float* __restrict__ P0, const float* __restrict__ Q0, f
         // ---- phase B: (row, chunk) items from the staged rows
         const int rows = min(T, ny - a);
         if (b_active && br < rows) {
-            ACC win[W];
+            ACC win[WB];
             auto load_window = [&](int arr) {
-                const double* src = stage + (arr * T + br) * RS;
+                const double* src = stage + (arr * T + br) * RS + bc * CW;
 #pragma unroll
-                for (int q = 0; q < W; ++q) win[q] = (ACC)src[yz_slot(br, bc * 8 + q)];
+                for (int q = 0; q < WB; ++q) win[q] = (ACC)src[q];
             };
-            float gs[T], t3[T], t2[T], t1[T];
+            float gs[CW], t3[CW], t2[CW], t1[CW];
             load_window(0);
-            conv_both_rows<R, T, ACC>(win, w, gs, t3);
+            conv_both_rows<R, CW, ACC>(win, w, gs, t3);
             load_window(1);
-            conv_g_rows<R, T, ACC>(win, w, t2);
+            conv_g_rows<R, CW, ACC>(win, w, t2);
             load_window(2);
-            conv_g_rows<R, T, ACC>(win, w, t1);
+            conv_g_rows<R, CW, ACC>(win, w, t1);
 #pragma unroll
-            for (int t = 0; t < T; ++t) {
+            for (int t = 0; t < CW; ++t) {
                 const float lap = __fadd_rn(__fadd_rn(t1[t], t2[t]), t3[t]);
                 float m = __fmul_rn(-lap, scale);
                 if (m < 0.f) m = 0.f;
-                sout[(0 * T + br) * OS + bc * 9 + t] = m;
-                sout[(1 * T + br) * OS + bc * 9 + t] = gs[t];
+                sout[(0 * T + br) * OS + bc * CW + t] = m;
+                sout[(1 * T + br) * OS + bc * CW + t] = gs[t];
             }
         }
         __syncthreads();
         // ---- phase C: coalesced row segments
         if (tid < TZ && z0 + tid < nz) {                          // thread = column: every row is one coalesced segment
-            const float* so = sout + tid + (tid >> 3);
+            const float* so = sout + tid;
             float* lo_p = log_out + plane + (long long)a * nz + z0 + tid;
             float* ga_p = gauss_out + plane + (long long)a * nz + z0 + tid;
 #pragma unroll
