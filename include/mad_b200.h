@@ -233,7 +233,8 @@ int mad_exclusive_scan_i32_to_i64(const int32_t* in, int n, int64_t* out, int64_
 /* One-pass threshold matching on the uint8 tcgen05 kernel (the product path): every pair with
  * cosine > cc is appended, unordered, to cand_key[] (an opaque sort key) and cand_dot[] = exact integer
  * dot product; *count (device, reset by the call) receives the number of pairs FOUND, which may
- * exceed cap -- then only cap were stored and the caller repeats with a larger buffer.
+ * exceed cap -- then only cap were stored and the caller repeats with a larger buffer; a value >= 2^62 reports an
+ * internal time-out of the kernel (the list is incomplete and must be discarded).
  * (cand_key holds hi * lo_rows + lo, the row-major rank of the pair.)
  * mad_match_pairs_finish sorts the n stored candidates by (hi, lo) -- the row-major order of
  * np.where(preds > cc), mad/MaD.py:423-424 -- and evaluates the float64 scores. */

@@ -44,6 +44,8 @@ constexpr uint32_t A_BYTES = KBLOCKS * KB_BYTES;    // 128 KB resident hi tile
 constexpr int EPI_WARPS = 8;       // two epilogue groups of 4 warps (one per TMEM lane quadrant), alternating tiles
 constexpr int THREADS = 128 + 32 * EPI_WARPS;
 constexpr uint32_t TMEM_COLS = 512;
+// count value a hand-off time-out leaves behind: the host raises instead of returning a truncated pair list
+constexpr unsigned long long MAD_MATCH_TIMEOUT_COUNT = 1ull << 62;
 constexpr int STG = 96;            // staged candidates per epilogue warp
 constexpr size_t STG_BYTES = (size_t)EPI_WARPS * STG * (sizeof(unsigned long long) + sizeof(int));
 constexpr size_t RB_BYTES = (size_t)2 * 2 * 256 * sizeof(float);          // per epilogue group, double-buffered 1/|lo| of a tile
@@ -390,6 +392,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 if (done == 4) break;                                // flags read BEFORE the scan that found nothing
                 __nanosleep(200);
             }
+            if (spins == (1LL << 27) - 1 && lane == 0) atomicExch(a.count, MAD_MATCH_TIMEOUT_COUNT);   // fail loudly on the host
         }
     } else if (warp >= 4) {
         // ===================== epilogue: thread = one hi row =====================
@@ -429,6 +432,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                     s_half[2 * ew + cur] = n;
                     long long spins = 0;
                     while (s_half[2 * ew + (cur ^ 1)] != 0 && ++spins < (1LL << 27)) __nanosleep(100);   // other half still in use
+                    if (spins >= (1LL << 27)) atomicExch(a.count, MAD_MATCH_TIMEOUT_COUNT);              // fail loudly on the host
                 }
                 cur ^= 1;
                 __syncwarp();
