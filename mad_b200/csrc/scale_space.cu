@@ -536,14 +536,25 @@ log_pass_strided_kernel(const float* __restrict__ in0, const float* __restrict__
     const int q_end = a1 - a0 + 2 * R;             // samples this thread needs: q = pos - (a0 - R) in [0, q_end)
     float* my = ring + threadIdx.x;
     auto issue = [&](int grp) {
+        const int q0 = grp * T;
+        float* dst0 = my + ((q0 & (D - 1)) * NA) * 128;          // T divides D: the group's slots are consecutive
+        const int p0 = a0 - R + q0;                              // position of the group's first sample on the axis
+        if (p0 >= 0 && p0 + T <= n && q0 + T <= q_end) {         // interior: no reflection, one address per group
+            const long long off = base + (long long)p0 * inner;
 #pragma unroll
-        for (int i = 0; i < T; ++i) {
-            const int q = grp * T + i;
-            if (q < q_end) {
-                const long long off = base + (long long)mad_reflect(a0 - R + q, n) * inner;
-                float* dst = my + ((q & (D - 1)) * NA) * 128;
-                cp_async4(dst, in0 + off);
-                if (MODE == 1) cp_async4(dst + 128, in1 + off);
+            for (int i = 0; i < T; ++i) {
+                cp_async4(dst0 + i * NA * 128, in0 + off + (long long)i * inner);
+                if (MODE == 1) cp_async4(dst0 + i * NA * 128 + 128, in1 + off + (long long)i * inner);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < T; ++i) {
+                const int q = q0 + i;
+                if (q < q_end) {
+                    const long long off = base + (long long)mad_reflect(a0 - R + q, n) * inner;
+                    cp_async4(dst0 + i * NA * 128, in0 + off);
+                    if (MODE == 1) cp_async4(dst0 + i * NA * 128 + 128, in1 + off);
+                }
             }
         }
         cp_async_commit();
