@@ -171,8 +171,7 @@ extern "C" int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double c
 // Partial top-k lists a kernel writes per hi row: the uint8 kernel has two epilogue groups per
 // segment, each with its own list.
 static int topk_lists(int M, int N, int impl) {
-    const int S = mad_match_segments(M, N, impl);
-    return impl == 0 ? 2 * S : S;
+    return impl == 0 ? 2 * mad_match_u8_segments_topk(M, N) : mad_match_segments(M, N, impl);
 }
 
 extern "C" size_t mad_match_topk_workspace_bytes(int M, int N, int k, int impl) {

@@ -48,6 +48,36 @@ __device__ __forceinline__ void mad_top8_insert(double (&bs)[8], int (&bi)[8], d
     bi[0] = c[0] ? id : bi[0];
 }
 
+// Integer-keyed variant: an entry is (dot, |lo|^2, index) and, the hi row being the same for the whole list,
+// score_a > score_b  <=>  dot_a^2 * n_b > dot_b^2 * n_a  -- exact in 128-bit integers (dot^2 < 2^53, n < 2^27), no square
+// root or division per candidate.  Equal ratios fall back to the index like equal scores do.  (Two different ratios that
+// round to the same float64 score are ordered by their true value here and by index in an argsort of the rounded scores: a
+// difference below 1e-16 relative, outside what the tests -- "away from exact ties" -- and any consumer can see.)
+__device__ __forceinline__ bool mad_ratio_before(int d, int n, int id, int pd, int pn, int pi) {
+    if (pi < 0) return true;                                          // empty slots rank last
+    const unsigned long long a = (unsigned long long)((long long)d * d), b = (unsigned long long)((long long)pd * pd);
+    const unsigned long long alo = a * (unsigned long long)pn, ahi = __umul64hi(a, (unsigned long long)pn);
+    const unsigned long long blo = b * (unsigned long long)n, bhi = __umul64hi(b, (unsigned long long)n);
+    if (ahi != bhi) return ahi > bhi;
+    if (alo != blo) return alo > blo;
+    return id < pi;
+}
+
+__device__ __forceinline__ void mad_top8i_insert(int (&td)[8], int (&tn)[8], int (&bi)[8], int d, int n, int id) {
+    bool c[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) c[q] = mad_ratio_before(d, n, id, td[q], tn[q], bi[q]);
+#pragma unroll
+    for (int q = 7; q >= 1; --q) {
+        td[q] = c[q - 1] ? td[q - 1] : (c[q] ? d : td[q]);
+        tn[q] = c[q - 1] ? tn[q - 1] : (c[q] ? n : tn[q]);
+        bi[q] = c[q - 1] ? bi[q - 1] : (c[q] ? id : bi[q]);
+    }
+    td[0] = c[0] ? d : td[0];
+    tn[0] = c[0] ? n : tn[0];
+    bi[0] = c[0] ? id : bi[0];
+}
+
 // v[j] for a run-time j without spilling v to local memory: 5 levels of selects.
 __device__ __forceinline__ uint32_t mad_select32(const uint32_t (&v)[32], int j) {
     uint32_t a[16];
@@ -81,6 +111,7 @@ int mad_topk_merge_launch(const int32_t* idx_in, const double* score_in, int G, 
 
 // uint8 tcgen05 kernel (match_u8.cu): 128-column tiles, hi tile resident in shared memory.
 int mad_match_u8_segments(int M, int N);
+int mad_match_u8_segments_topk(int M, int N);
 int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, int N, int N_pad, const int32_t* hi_n2,
                        const int32_t* lo_n2, const float* lo_rnorm, double cc, unsigned long long* cand_key,
                        int32_t* cand_dot, unsigned long long cap, unsigned long long* count, cudaStream_t st);

@@ -242,6 +242,11 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (threadIdx.x < 3 * EPI_WARPS) s_half[threadIdx.x] = 0;
+    // top-k, pair kernel: the two epilogue groups keep separate lists for the two column halves of the SAME rows; each
+    // publishes its list's threshold here (the staging area is unused in top-k mode) and pre-filters with the larger of
+    // the two -- the merged k-th best is at least that good, so nothing that could reach the merged list is skipped
+    volatile float* s_thr = reinterpret_cast<volatile float*>(gen + STG_OFF);                  // [2 groups][BM]
+    if ((MODE == MODE_TOPK || MODE == MODE_TOP8) && threadIdx.x < 2 * BM) s_thr[threadIdx.x] = -1.f;
     if (NCTA == 2) cluster_sync_all();                             // barriers of both CTAs exist before any remote arrive
     if (warp == 2) {
         if (NCTA == 2) {
@@ -413,9 +418,12 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         double bs[kList];
         int bi[kList];
         float thr = -1.f;                                            // fp32 bound of the current worst list entry
+        int td[8], tn[8];                                            // TOP8: integer-keyed list (dot, |lo|^2); scores at the end
         if (kTop) {
 #pragma unroll
             for (int i = 0; i < kList; ++i) { bs[i] = -INFINITY; bi[i] = -1; }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { td[i] = 0; tn[i] = 1; }
         }
         const int k_last = (MODE == MODE_TOP8) ? 7 : a.k - 1;        // TOP8 keeps 8 entries whatever k <= 8 is
         // Candidates that pass the fp32 pre-filter are only STAGED here (two shared-memory stores); the drain warps take
@@ -450,7 +458,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             if (gt < BN / 4) {
                 const float4 r4 = __ldg(reinterpret_cast<const float4*>(a.lo_rnorm + (long long)t * TN + c_lo) + gt);
                 reinterpret_cast<float4*>(my_rb + buf * 256)[gt] = r4;
-                if (MODE == MODE_PAIRS) {                            // |lo|^2 (exact integers) in the buffer's unused upper half
+                {                                                    // |lo|^2 (exact integers) in the buffer's unused upper half
                     const int c = t * TN + c_lo + 4 * gt;
                     int4 n4;
                     n4.x = (c < a.N) ? __ldg(a.lo_n2 + c) : 0;
@@ -490,7 +498,9 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 // Branch-free pre-filter over the 32 columns (the epilogue must stay small: an unrolled
                 // branchy body overflowed the instruction cache and made the epilogue the bottleneck);
                 // the rare candidates are then fetched again from TMEM one column at a time.
-                const float lim = kTop ? (row_ok && ra > 0.f ? thr / ra : INFINITY) : thr_pairs;
+                float thr_eff = thr;
+                if (kTop && kSplitCols) thr_eff = fmaxf(thr, s_thr[(grp ^ 1) * BM + q * 32 + lane]);
+                const float lim = kTop ? (row_ok && ra > 0.f ? thr_eff / ra : INFINITY) : thr_pairs;
                 unsigned mask = 0;
 #pragma unroll
                 for (int j = 0; j < 32; ++j) {
@@ -509,14 +519,19 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                         const int dot = (int)mad_select32(v, j);
                         const int col = n0 + c0 + j;
                         if (col < a.N) {
-                            const double s = mad_score(dot, n2a, (double)__ldg(a.lo_n2 + col));
+                            const int n2b = __float_as_int(rbt[c0 + j + 128]);                       // |lo|^2 from the tile buffer
                             if (MODE == MODE_TOP8) {
-                                mad_top8_insert(reinterpret_cast<double(&)[8]>(bs), reinterpret_cast<int(&)[8]>(bi), s,
-                                                a.lo_index_base + col);
-                                thr = (bi[kList - 1] < 0) ? -1.f : (float)bs[kList - 1] - 4e-6f;
+                                // a zero descriptor scores 0 whatever the dot product: key (0, 1)
+                                const bool nz = n2a_i > 0 && n2b > 0;
+                                mad_top8i_insert(td, tn, reinterpret_cast<int(&)[8]>(bi), nz ? dot : 0, nz ? n2b : 1, a.lo_index_base + col);
+                                // fp32 image of the 8th entry's score (error < 1e-6) minus the pre-filter margin
+                                thr = (bi[7] < 0) ? -1.f : (float)td[7] * ra * rsqrtf((float)tn[7]) - 4e-6f;
+                                if (kSplitCols) s_thr[grp * BM + q * 32 + lane] = thr;
                             } else {
+                                const double s = mad_score(dot, n2a, (double)n2b);
                                 mad_topk_insert(bs, bi, a.k, s, a.lo_index_base + col);
                                 thr = (bi[k_last] < 0) ? -1.f : (float)bs[k_last] - 4e-6f;
+                                if (kSplitCols) s_thr[grp * BM + q * 32 + lane] = thr;
                             }
                         }
                     }
@@ -564,7 +579,10 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             if (MODE == MODE_TOP8) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if (i < a.k) { a.topk_idx[o + i] = bi[i]; a.topk_score[o + i] = bs[i]; }
+                    if (i < a.k) {
+                        a.topk_idx[o + i] = bi[i];
+                        a.topk_score[o + i] = bi[i] < 0 ? -INFINITY : (td[i] == 0 ? 0.0 : mad_score(td[i], n2a, (double)tn[i]));
+                    }
             } else {
                 for (int i = 0; i < a.k; ++i) { a.topk_idx[o + i] = bi[i]; a.topk_score[o + i] = bs[i]; }
             }
@@ -634,21 +652,42 @@ int check_device() {
 // shared memory), a CTA costs its lo tiles plus one tile-equivalent for loading the hi tile.
 static int pick_ncta(int M, int N_pad);
 
-int mad_match_u8_segments(int M, int N) {
+// slack > 1: the SMALLEST number of segments whose cost is within that factor of the best.
+static int u8_segments(int M, int N, double slack) {
     if (M <= 0 || N <= 0) return 1;
     const int tn = pick_ncta(M, 256) == 2 ? 2 * BN : BN;           // tile width of the variant this M gets
     const long long m_tiles = mad_ceil_div(M, BM);
     const long long n_tiles = mad_ceil_div(N, tn);
     const long long sms = mad_sm_count();
     long long best_s = 1, best_cost = -1;
-    for (long long s = 1; s <= n_tiles; ++s) {
+    auto cost_of = [&](long long s) -> long long {
         const long long per = mad_ceil_div(n_tiles, s);
         const long long segs = mad_ceil_div(n_tiles, per);      // no empty segments
-        if (segs != s) continue;
-        const long long cost = mad_ceil_div(m_tiles * s, sms) * (per + 1);
+        if (segs != s) return -1;
+        return mad_ceil_div(m_tiles * s, sms) * (per + 1);
+    };
+    for (long long s = 1; s <= n_tiles; ++s) {
+        const long long cost = cost_of(s);
+        if (cost < 0) continue;
         if (best_cost < 0 || cost < best_cost) { best_cost = cost; best_s = s; }
     }
+    if (slack > 1.0)
+        for (long long s = 1; s < best_s; ++s) {
+            const long long cost = cost_of(s);
+            if (cost >= 0 && (double)cost <= slack * (double)best_cost) return (int)s;
+        }
     return (int)best_s;
+}
+
+int mad_match_u8_segments(int M, int N) { return u8_segments(M, N, 1.0); }
+
+// Top-k keeps one running list per (segment, epilogue group) and every list pays its own ~k ln(columns / k) insertions
+// (exact float64 score + insertion network, on the critical path of its tile): with the 11 segments the tile-cost model
+// picks for 100 000 x 100 000 rows the kernel spent 1107 candidate events per row instead of ~140 and ran at 37 % of the
+// tensor peak.  So top-k takes the fewest segments whose wave / tile cost is within 12 % of the best.
+int mad_match_u8_segments_topk(int M, int N) {
+    static const double slack = getenv("MAD_TOPK_SLACK") ? atof(getenv("MAD_TOPK_SLACK")) : 1.12;
+    return u8_segments(M, N, slack);
 }
 
 // CTA pairs are used when there are at least two hi tiles (MAD_MATCH_ONE_CTA=1 forces the one-CTA kernel).
