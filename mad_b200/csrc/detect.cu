@@ -206,6 +206,14 @@ __global__ void scatter_kernel(const MadKeypoint* __restrict__ cand, const int* 
     if (i == n - 1) *out_count = pos[i] + flags[i];
 }
 
+struct KeyLess {
+    __device__ __forceinline__ bool operator()(unsigned long long a, unsigned long long b) const { return a < b; }
+};
+
+// Candidate lists are small (10^3 - 10^5 entries): an 8-pass radix sort of 64-bit keys is eight launch-bound passes
+// (~90 us at C2); a merge sort is one block sort plus log2(n / tile) merge passes.
+constexpr int kMergeSortMax = 1 << 20;
+
 struct SortLayout {
     size_t keys_in, keys_out, idx_in, idx_out, flags, pos, cub, total;
 };
@@ -222,6 +230,9 @@ SortLayout sort_layout(int n) {
     cub::DeviceRadixSort::SortPairs(nullptr, a, (const unsigned long long*)nullptr, (unsigned long long*)nullptr,
                                     (const int*)nullptr, (int*)nullptr, (int)nn);
     cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, (int)nn);
+    size_t c = 0;
+    cub::DeviceMergeSort::SortPairs(nullptr, c, (unsigned long long*)nullptr, (int*)nullptr, (int)nn, KeyLess());
+    a = a > c ? a : c;
     l.cub = take(a > b ? a : b);
     l.total = o;
     return l;
@@ -276,7 +287,11 @@ extern "C" int mad_sort_keypoints(const MadKeypoint* cand, int n, const int* dim
         MAD_LAUNCH_OK();
     }
     size_t cub_bytes = l.total - l.cub;
-    {
+    if (n <= kMergeSortMax) {                                        // in place: the order ends up in idx_in
+        MAD_PROF("cub_merge_sort_pairs", st);
+        MAD_CUDA(cub::DeviceMergeSort::SortPairs(ws + l.cub, cub_bytes, keys_in, idx_in, n, KeyLess(), st));
+        idx_out = idx_in;
+    } else {
         MAD_PROF("cub_radix_sort_pairs", st);
         MAD_CUDA(cub::DeviceRadixSort::SortPairs(ws + l.cub, cub_bytes, keys_in, keys_out, idx_in, idx_out, n, 0, 64, st));
     }
