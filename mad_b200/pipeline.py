@@ -498,6 +498,8 @@ class HostStage(object):
         n = t.numel() * t.element_size()
         buf = self.bufs.get(name)
         if buf is None or buf.numel() < n:
+            if buf is not None:
+                self.keep.append(buf)      # a copy kernel may still be writing into the old buffer: free it after the wait
             buf = torch.empty(max(n * 5 // 4, 256), dtype=torch.uint8).pin_memory()
             self.bufs[name] = buf
         view = buf[:n].view(t.dtype).view(t.shape)
@@ -576,6 +578,9 @@ class MapStream(object):
         of those synchronises the device: 16 ms per C2 map instead of 8.3.)"""
         if isinstance(grid, np.ndarray):
             grid = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float32))
+        if self.n_up - self.n >= len(self.gbuf):
+            raise _lib.MadError("MapStream.upload: %d uploads are waiting for submit(); the %d upload buffers are all in use"
+                                % (self.n_up - self.n, len(self.gbuf)))
         k = self.n_up % len(self.gbuf)
         self.n_up += 1
         dev = torch.device("cuda", torch.cuda.current_device())
