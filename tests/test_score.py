@@ -151,3 +151,33 @@ def test_device_refine_batch_and_recovery():
     before = np.sqrt(np.mean(np.sum((moved - atoms) ** 2, axis=1)))
     after = np.sqrt(np.mean(np.sum((out[0] - atoms) ** 2, axis=1)))
     assert conv[0] and after < 0.25 * before, (before, after)
+
+
+def test_host_common_box_equals_oracle_bounds():
+    """The host-side bounds of Dmap._common_box (what mad_box_scores is launched with) against the oracle's restatement
+    of mad/Dmap.py:172-241 on random integer and half-integer offsets (CPU only)."""
+    import score_oracle as so
+    from mad_b200.Dmap import Dmap
+    rng = np.random.default_rng(3)
+    n_checked = 0
+    for _ in range(400):
+        s1 = [int(v) for v in rng.integers(3, 40, 3)]
+        s2 = [int(v) for v in rng.integers(3, 40, 3)]
+        o1 = [float(v) for v in rng.integers(-15, 15, 3)]
+        o2 = [float(v) for v in rng.integers(-15, 15, 3)]
+        want = so.common_box(o1, s1, o2, s2)
+        try:
+            got = Dmap._common_box(o1, s1, o2, s2)
+        except ValueError:
+            got = "mismatch"
+        if want is None:
+            assert got is None
+            continue
+        g1 = np.zeros(s1)[tuple(slice(b[0], b[2]) for b in want)]
+        g2 = np.zeros(s2)[tuple(slice(b[1], b[3]) for b in want)]
+        if g1.shape != g2.shape:                       # the reference's np.dot would raise on such boxes
+            assert got == "mismatch"
+            continue
+        assert got[:3] == [b[0] for b in want] and got[3:6] == [b[1] for b in want] and got[6:] == list(g1.shape)
+        n_checked += 1
+    assert n_checked > 60
