@@ -158,7 +158,7 @@ class Dmap(object):
     def _common_box(o1, s1, o2, s2):
         """Bounds of the common box as the reference rounds them (mad/Dmap.py:172-241); origins in voxels.
         Returns [x1, y1, z1, x2, y2, z2, ex, ey, ez] or None when an extent is negative."""
-        lo1, lo2, ext = [], [], []
+        bounds = []
         for a in range(3):
             i1, i2, b1, b2 = o1[a], o2[a], s1[a], s2[a]
             if i1 > i2:
@@ -173,8 +173,11 @@ class Dmap(object):
                 mx1, mx2 = int(round(b1)), int(round(i1 + b1 - i2))
             else:
                 mx1, mx2 = int(round(b1)), int(round(b2))
-            if mx1 - mn1 < 0:
-                return None
+            bounds.append((mn1, mn2, mx1, mx2))
+        if any(mx1 - mn1 < 0 for mn1, _, mx1, _ in bounds):       # mad/Dmap.py:239-241, tested before any slicing
+            return None
+        lo1, lo2, ext = [], [], []
+        for a, (mn1, mn2, mx1, mx2) in enumerate(bounds):
             # NumPy slicing clips both boxes to their arrays; the two extents agree except for rounding at x.5 offsets
             e1 = max(0, min(mx1, s1[a]) - mn1)
             e2 = max(0, min(mx2, s2[a]) - mn2)

@@ -160,11 +160,11 @@ def test_host_common_box_equals_oracle_bounds():
     from mad_b200.Dmap import Dmap
     rng = np.random.default_rng(3)
     n_checked = 0
-    for _ in range(400):
+    for _ in range(1200):
         s1 = [int(v) for v in rng.integers(3, 40, 3)]
         s2 = [int(v) for v in rng.integers(3, 40, 3)]
-        o1 = [float(v) for v in rng.integers(-15, 15, 3)]
-        o2 = [float(v) for v in rng.integers(-15, 15, 3)]
+        o1 = [float(v) / 2 for v in rng.integers(-30, 30, 3)]       # integer and half-integer voxel offsets
+        o2 = [float(v) / 2 for v in rng.integers(-30, 30, 3)]
         want = so.common_box(o1, s1, o2, s2)
         try:
             got = Dmap._common_box(o1, s1, o2, s2)
