@@ -16,13 +16,16 @@
 //                              lo k-blocks into a 5-stage ring (mbarrier complete_tx)
 //   warp 1      MMA issuer   : tcgen05.mma.cta_group::1.kind::i8, M=128 N=128 K=32, int32
 //                              accumulators in TMEM (4 x 128 columns, 4-deep)
-//   warp 2      TMEM allocator
+//   warp 2      TMEM allocator; warps 2 and 3 DRAIN the pair list in PAIRS mode (float64 decision, output
+//               reservation, copy-out of the half buffers the epilogue warps publish)
 //   warps 4..11 epilogue     : two groups of 4 warps alternating tiles; tcgen05.ld (32 lanes x 32
 //                              columns), thread = one hi row
 //        PAIRS mode: hits (row, col, dot) are staged per warp in shared memory and appended to a
 //                    global candidate list by the drain warps (one atomicAdd per half buffer); a radix sort by
 //                    (row, col) afterwards restores np.where's row-major order (match_finish).
-//        TOPK mode : per-row running top-k in the thread, one partial list per lo segment.
+//        TOPK mode : per-row running top-k in the thread (k <= 8: a register list keyed by the exact integer ratio
+//                    dot^2 / |lo|^2), one partial list per (lo segment, epilogue group), thresholds of the two groups
+//                    shared through shared memory.
 #include <cuda.h>
 #include <stdlib.h>
 
