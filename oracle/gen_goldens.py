@@ -372,6 +372,15 @@ def main(which):
         d = bare_dmap(g_map, 2.0, m_org)
         d.mask_with(bare_dmap(g_sub, 2.0, far))
         out["masked_far"] = d.grid3d.copy()
+        # PDB manipulation helpers used around the refinement (mad/PDB.py:80-128): written file and RMSDs
+        pa, pb = PDB(pdb_path), PDB(pdb_path)
+        pb.set_coords(moved)
+        pb.rotate_atoms(euler_rod_mat([0, 0, 1], 0.3))
+        pb.translate_atoms([1.25, -2.5, 3.75])
+        wpath = os.path.join(WORK, "score_written.pdb")
+        pb.write_pdb(wpath)
+        out["pdb_written"] = np.frombuffer(open(wpath, "rb").read(), dtype=np.uint8)
+        out["pdb_rmsd"] = np.array([pa.get_rmsd_with(pb), pa.get_rmsdCA_with(pb)], dtype=np.float64)
         np.savez_compressed(os.path.join(GOLD, "score.npz"), **out)
         print("wrote score.npz", {k: (v.shape if v.ndim else float(v)) for k, v in out.items() if k != "pdb_text"})
     if "c1" in which:

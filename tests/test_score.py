@@ -181,3 +181,20 @@ def test_host_common_box_equals_oracle_bounds():
         assert got[:3] == [b[0] for b in want] and got[3:6] == [b[1] for b in want] and got[6:] == list(g1.shape)
         n_checked += 1
     assert n_checked > 60
+
+
+def test_pdb_helpers_equal_reference(tmp_path):
+    """PDB.rotate_atoms / translate_atoms / write_pdb / rmsd (host glue, mad/PDB.py:80-128) against the reference's output."""
+    from mad_b200.PDB import PDB
+    from mad_b200.math_utils import euler_rod_mat
+    g = H.golden("score")
+    path = os.path.join(str(tmp_path), "case.pdb")
+    open(path, "wb").write(bytes(g["pdb_text"]))
+    pa, pb = PDB(path), PDB(path)
+    pb.set_coords(g["moved"])
+    pb.rotate_atoms(euler_rod_mat([0, 0, 1], 0.3))
+    pb.translate_atoms([1.25, -2.5, 3.75])
+    out = os.path.join(str(tmp_path), "written.pdb")
+    pb.write_pdb(out)
+    assert open(out, "rb").read() == bytes(g["pdb_written"])
+    assert np.allclose([pa.get_rmsd_with(pb), pa.get_rmsdCA_with(pb)], g["pdb_rmsd"], rtol=1e-14, atol=0)
