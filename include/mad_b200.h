@@ -219,8 +219,9 @@ int mad_dsc_to_half(const int16_t* dsc, int rows, int rows_padded, void* half_ou
  * FILL writes pair_hi / pair_lo / pair_score starting at seg_offset[i][s], lo ascending -- i.e. the
  * row-major order of np.where(preds > cc) (mad/MaD.py:423-424).
  * impl: 1 = SIMT integer kernel (device-side check), 2 = fp16 tcgen05 kernel (entries <= 2048).
- * The product path for threshold matching is the ONE-pass mad_match_pairs below (impl 0 here is
- * accepted as an alias of 2). */
+ * The product path for threshold matching is the ONE-pass mad_match_pairs below; impl 0 (that kernel) has no
+ * count / fill form and is REJECTED here with MAD_ERR_ARG and a message (never silently remapped).
+ * mad_match_segments(M, N, 0) only sizes the top-k workspace of the uint8 kernel. */
 int mad_match_segments(int M, int N, int impl);
 int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, int32_t* seg_count, int impl,
                     void* stream);

@@ -81,8 +81,8 @@ class FeatureList(list):
     _signature = None
 
     def stamp(self):
-        self._signature = (len(self), tuple(id(x) for x in self[:4]), tuple(id(x) for x in self[-4:]))
+        self._signature = tuple(id(x) for x in self)          # every element: an edit anywhere in the list is seen
         return self
 
     def unchanged(self):
-        return self._signature == (len(self), tuple(id(x) for x in self[:4]), tuple(id(x) for x in self[-4:]))
+        return self._signature == tuple(id(x) for x in self)

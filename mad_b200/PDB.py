@@ -32,6 +32,22 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+def write_situs(outname, grid, voxelsp, dxi, dyi, dzi):
+    """Situs text map exactly as the reference writes it (mad/PDB.py:165-179): header line, blank line, then the voxels
+    x-fastest, a line break before every 10th value."""
+    dxb, dyb, dzb = grid.shape
+    with open(outname, "w") as f:
+        f.write("%f %f %f %f %i %i %i\n\n" % (voxelsp, dxi, dyi, dzi, dxb, dyb, dzb))
+        voxi = 0
+        for z in range(dzb):
+            for y in range(dyb):
+                for x in range(dxb):
+                    if (voxi + 1) % 10 == 0:
+                        f.write("\n")
+                    f.write("   %6.6f   " % grid[x][y][z])
+                    voxi += 1
+
+
 class PDB(object):
     def __init__(self, pdb_file):
         self.pdb_file = pdb_file
@@ -180,17 +196,7 @@ class PDB(object):
         if outname != "":
             ext = os.path.splitext(outname)[-1].lower()
             if ext in [".sit", ".situs"]:
-                dxb, dyb, dzb = grid.shape
-                with open(outname, "w") as f:
-                    f.write("%f %f %f %f %i %i %i\\n\\n" % (voxelsp, dxi, dyi, dzi, dxb, dyb, dzb))
-                    voxi = 0
-                    for z in range(dzb):
-                        for y in range(dyb):
-                            for x in range(dxb):
-                                if (voxi + 1) % 10 == 0:
-                                    f.write("\\n")
-                                f.write("   %6.6f   " % grid[x][y][z])
-                                voxi += 1
+                write_situs(outname, grid, voxelsp, dxi, dyi, dzi)
             else:
                 _mrc.write_mrc(outname, grid.transpose(2, 1, 0), voxelsp, origin=(dxi, dyi, dzi))
         return grid.astype(np.float32), dxi, dyi, dzi

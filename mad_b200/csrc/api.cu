@@ -125,8 +125,9 @@ static int run_match(const MadDscSet* hi, const MadDscSet* lo, double cc, int mo
                         mode, S, seg_count, seg_offset, pair_hi, pair_lo, pair_score, k, base, topk_idx, topk_score, st);
 }
 
-// Segment count: impl 0 = the uint8 kernel's (128-column tiles); 1 and 2 share the fp16 kernel's
-// choice (256-column tiles, same output layout).
+// Segment count of the two-pass count / fill kernels (impl 1 and 2 share the fp16 kernel's choice: 256-column tiles,
+// same output layout).  impl 0 (one-pass uint8 kernel) has no count / fill form: mad_match_count / mad_match_fill reject
+// it; the value returned for impl 0 only sizes the top-k workspace of that kernel.
 extern "C" int mad_match_segments(int M, int N, int impl) {
     return impl == 0 ? mad_match_u8_segments(M, N) : mad_match_tc_segments(M, N);
 }
@@ -140,7 +141,11 @@ static int check_segments(const MadDscSet* hi, const MadDscSet* lo, int n_seg) {
 
 extern "C" int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, int32_t* seg_count,
                                int impl, void* stream) {
-    if (impl == 0) impl = 2;
+    if (impl == 0) {
+        mad_set_error("%s: impl 0 (the one-pass uint8 tcgen05 kernel) has no count/fill form -- call mad_match_pairs + "
+                      "mad_match_pairs_finish; count/fill serve impl 1 (SIMT check) and 2 (fp16 tcgen05)", "mad_match_count");
+        return MAD_ERR_ARG;
+    }
     int rc = check_sets(hi, lo, impl);
     if (rc != MAD_OK) return rc;
     if (hi->rows == 0) return MAD_OK;
@@ -157,7 +162,11 @@ extern "C" int mad_match_count(const MadDscSet* hi, const MadDscSet* lo, double 
 
 extern "C" int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double cc, int n_seg, const int64_t* seg_offset,
                               int32_t* pair_hi, int32_t* pair_lo, double* pair_score, int impl, void* stream) {
-    if (impl == 0) impl = 2;
+    if (impl == 0) {
+        mad_set_error("%s: impl 0 (the one-pass uint8 tcgen05 kernel) has no count/fill form -- call mad_match_pairs + "
+                      "mad_match_pairs_finish; count/fill serve impl 1 (SIMT check) and 2 (fp16 tcgen05)", "mad_match_fill");
+        return MAD_ERR_ARG;
+    }
     int rc = check_sets(hi, lo, impl);
     if (rc != MAD_OK) return rc;
     if (hi->rows == 0 || lo->rows == 0) return MAD_OK;

@@ -98,9 +98,11 @@ def run_pipeline(mrc_path, patch_size=16, want_hist=False):
     return ms, anchors, described, t
 
 
-def pack_case(name, q, voxelsp, origin, ms, anchors, described, timings, full_dsc=True):
+def collect_case(q, voxelsp, origin, ms, anchors, described, timings, full_dsc=True):
+    """Everything a fixture stores about one reference run, as a dict of arrays (+ the descriptors)."""
     out = {}
-    out["input_q"] = q
+    if q is not None:
+        out["input_q"] = q
     out["voxelsp"] = np.array(voxelsp, dtype=np.float64)
     out["origin"] = np.array(origin, dtype=np.float64)
     out["ms_origin"] = np.array([ms.xi, ms.yi, ms.zi], dtype=np.float64)
@@ -149,6 +151,11 @@ def pack_case(name, q, voxelsp, origin, ms, anchors, described, timings, full_ds
         out["dsc"] = dsc
     out["ref_timings_s"] = np.array([timings[k] for k in ("build_space", "find_anchors",
                                                          "assign_orientations", "generate_descriptors")])
+    return out, dsc
+
+
+def pack_case(name, q, voxelsp, origin, ms, anchors, described, timings, full_dsc=True):
+    out, dsc = collect_case(q, voxelsp, origin, ms, anchors, described, timings, full_dsc)
     path = os.path.join(GOLD, name + ".npz")
     np.savez_compressed(path, **out)
     print("wrote %s  K=%d D=%d  (%.1f KB)  timings=%s" % (path, len(anchors), len(described),
@@ -301,6 +308,10 @@ def main(which):
             g, dxi, dyi, dzi = PDB(pdb_path).structure_to_density(**kw)
             out[tag + "_grid"] = g
             out[tag + "_origin"] = np.array([dxi, dyi, dzi], dtype=np.float64)
+            if tag == "c":                                      # the reference's Situs writer (mad/PDB.py:165-179)
+                sit_path = os.path.join(WORK, "density_case_c.sit")
+                PDB(pdb_path).structure_to_density(outname=sit_path, **kw)
+                out["c_sit_text"] = np.frombuffer(open(sit_path, "rb").read(), dtype=np.uint8)
         np.savez_compressed(os.path.join(GOLD, "density.npz"), **out)
         print("wrote density.npz", {k: v.shape for k, v in out.items()})
     if "score" in which:

@@ -196,3 +196,43 @@ def synthetic_descriptors(m, seed, noisy_copy_of=None, copy_frac=0.5, redraw=0.1
                           fresh(m - n_copy).reshape(m - n_copy, 1024)])
     perm = rng.permutation(m)
     return out[perm]
+
+
+# ---------------------------------------------------------------------------------------------
+# The benchmark workloads (BASELINE.json configs): ONE definition shared by bench.py (inputs only),
+# the fixture generator (oracle/gen_golden_bench.py) and the parity tests, so that what is benchmarked is what is
+# pinned against the reference.
+# ---------------------------------------------------------------------------------------------
+C2 = dict(n=256, resolution=8.0, voxelsp=2.0, n_sub=6, atoms_per_sub=40000, seed0=10, box=150.0)
+
+
+def c2_inputs(rank=0):
+    """(256^3 assembly map, [6 component maps]) of config C2; rank r > 0 gets its own map (seeds shifted by 100 r)."""
+    cfg = dict(C2)
+    cfg["seed0"] = C2["seed0"] + 100 * int(rank)
+    return assembly_with_components(**cfg)
+
+
+C4_MAPS = 64
+
+
+def c4_snapshot(i, base=None):
+    """Snapshot i of config C4: the C1 component (9 000-atom walk, seed 1) with every atom displaced by
+    N(0, 1.5 A) (seed 100 + i), simulated at 4 A / 1 A per voxel and fitted to 96^3."""
+    if base is None:
+        base = random_walk_atoms(9000, 85.0, 1)
+    rng = np.random.default_rng(100 + int(i))
+    g, _ = simulate_density(base + rng.normal(scale=1.5, size=base.shape), 4.0, 1.0)
+    return fit_to_cube(g, 96)
+
+
+def c5_descriptor_sets(m, n):
+    """(hi int16[m,1024], lo int16[n,1024]) of config C5.  8192 distinct multinomial/Dirichlet rows, tiled with a
+    different cyclic shift per tile (keeps the host generation short); hi = 50 % noisy copies of lo rows."""
+    base = synthetic_descriptors(8192, 7)
+    reps = (n + len(base) - 1) // len(base)
+    rng = np.random.default_rng(11)
+    lo = np.concatenate([np.roll(base, int(rng.integers(0, 1024)), axis=1) if r else base for r in range(reps)])[:n]
+    hi = synthetic_descriptors(min(m, 8192), 8, noisy_copy_of=lo[:8192])
+    hi = np.concatenate([hi] * ((m + len(hi) - 1) // len(hi)))[:m]
+    return np.ascontiguousarray(hi), np.ascontiguousarray(lo)

@@ -60,3 +60,20 @@ def test_device_density_equals_reference(tmp_path, tag, kw):
     assert grid.max() == 1.0
     dev, *_ = pdb.structure_to_density_device(**kw)
     assert dev.is_cuda and np.array_equal(dev.cpu().numpy(), grid)
+
+
+def test_situs_writer_equals_reference_and_reads_back(tmp_path):
+    """``structure_to_density(outname="*.sit")``: the written text equals the reference's byte for byte
+    (mad/PDB.py:165-179) and this package's own readers (MapSpace / Dmap header + voxel parse) accept it."""
+    from mad_b200.PDB import write_situs
+    from mad_b200.MapSpace import MapSpace
+    g = H.golden("density")
+    grid, org = g["c_grid"], g["c_origin"]
+    path = os.path.join(str(tmp_path), "out.sit")
+    write_situs(path, grid, 2.0, float(org[0]), float(org[1]), float(org[2]))
+    assert open(path, "rb").read() == bytes(g["c_sit_text"])
+    ms = MapSpace(path)
+    back, origin = ms._load()                                     # host-side reader only (no device work)
+    assert back.shape == grid.shape and tuple(origin) == tuple(float(o) for o in org) and ms.voxelsp == 2.0
+    want = np.round(grid.astype(np.float64), 6)                   # "%6.6f" text, then max-normalised by the reader
+    assert np.abs(back - (want / want.max()).astype(np.float32)).max() <= 1e-6
