@@ -38,7 +38,9 @@ for _p in (REPO, os.path.join(REPO, "oracle")):
 
 import numpy as np  # noqa: E402
 
-C2 = dict(n=256, resolution=8.0, voxelsp=2.0, n_sub=6, atoms_per_sub=40000, seed0=10, box=150.0)
+import synth  # noqa: E402  (oracle/synth.py: input generators only)
+
+C2 = synth.C2
 CPU_SAMPLE_SIDE = 64
 METRIC = "voxels/sec scale-space+detect+describe(+match)"
 UNIT = "voxels/s"
@@ -234,14 +236,12 @@ def main():
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if "MAD_KEEP_NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL's log (NCCL_DEBUG is left to the caller) goes to a file or stderr, never to stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
 
     # ---- inputs: each rank its own map (independent units) ---------------------------------
-    cfg = dict(C2)
-    cfg["seed0"] = C2["seed0"] + 100 * rank
-    grid_h, comps_h = synth.assembly_with_components(**cfg)
+    grid_h, comps_h = synth.c2_inputs(rank)
     n_vox = int(grid_h.size)
     grid_pin = torch.from_numpy(grid_h).pin_memory()
     grid_d = grid_pin.to(dev)

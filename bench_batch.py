@@ -26,17 +26,15 @@ def main(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if "MAD_KEEP_NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL's log (NCCL_DEBUG is left to the caller) goes to a file or stderr, never to stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     n_maps = int(os.environ.get("MAD_C4_MAPS", "64"))
     base = synth.random_walk_atoms(9000, 85.0, 1)
     mine = par.assign_units(n_maps, rank, world)
     grids = []
     for i in mine:
-        rng = np.random.default_rng(100 + i)
-        g, _ = synth.simulate_density(base + rng.normal(scale=1.5, size=base.shape), 4.0, 1.0)
-        grids.append(synth.fit_to_cube(g, 96))
+        grids.append(synth.c4_snapshot(i, base))
     pins = [torch.from_numpy(g).pin_memory() for g in grids]
     devs = [p.to(dev) for p in pins]
     n_vox_total = n_maps * 96 ** 3

@@ -28,18 +28,12 @@ def main(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        if "MAD_KEEP_NCCL_DEBUG" not in os.environ:
-            os.environ["NCCL_DEBUG"] = "WARN"          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        # NCCL's log (NCCL_DEBUG is left to the caller) goes to a file or stderr, never to stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     M = N = int(os.environ.get("MAD_C5_ROWS", "100000"))
     k = 8
-    # identical inputs on every rank (same seeds); 8192 distinct rows tiled keep host generation short
-    base = synth.synthetic_descriptors(8192, 7)
-    reps = (N + len(base) - 1) // len(base)
-    rng = np.random.default_rng(11)
-    lo_h = np.concatenate([np.roll(base, int(rng.integers(0, 1024)), axis=1) if r else base for r in range(reps)])[:N]
-    hi_h = synth.synthetic_descriptors(min(M, 8192), 8, noisy_copy_of=lo_h[:8192])
-    hi_h = np.concatenate([hi_h] * ((M + len(hi_h) - 1) // len(hi_h)))[:M]
+    hi_h, lo_h = synth.c5_descriptor_sets(M, N)          # identical inputs on every rank (same seeds)
     s, e = par.shard_bounds(N, world)[rank]
     hi_pin = torch.from_numpy(hi_h).pin_memory()
     lo_pin = torch.from_numpy(np.ascontiguousarray(lo_h[s:e])).pin_memory()

@@ -6,7 +6,9 @@
 * all-pairs matching (``MaD.py:420-424``): the lo (reference) axis is cut into G contiguous shards,
   every rank holds all hi rows and computes its local top-k with GLOBAL lo indices; one
   ``all_gather`` of the [M, k] lists and a k-way merge with the (score desc, index asc) rule give
-  a result bit-identical to one GPU.
+  a result bit-identical to one GPU.  Threshold mode (the parity contract, ``MaD.py:423-424``): every rank lists its
+  pairs with GLOBAL lo indices; pair counts are all-gathered, the lists travel in one padded all-gather and are merged
+  in (hi, lo) order -- the row-major order of ``np.where`` on the whole score matrix.
 """
 import torch
 import torch.distributed as dist
@@ -71,3 +73,70 @@ def match_topk_sharded(hi_set, lo_shard_set, k, lo_index_base, group=None, impl=
     if idx_g.shape[0] == 1:
         return idx, sc
     return P.topk_merge(idx_g, sc_g)
+
+
+def merge_pair_lists(parts):
+    """[(hi int32 [P_r], lo_global int32 [P_r], score float64 [P_r])] in rank order (= ascending lo shards), each already in
+    (hi, lo) order -> one list in (hi, lo) order.  A stable sort by hi keeps, inside a hi row, the rank order and the
+    per-rank lo order, which is ascending global lo."""
+    hi = torch.cat([p[0] for p in parts])
+    lo = torch.cat([p[1] for p in parts])
+    sc = torch.cat([p[2] for p in parts])
+    if len(parts) == 1 or hi.numel() == 0:
+        return hi, lo, sc
+    order = torch.sort(hi, stable=True).indices
+    return hi[order], lo[order], sc[order]
+
+
+def gather_pair_lists(pair_hi, pair_lo_global, score, group=None):
+    """all-gather-v of per-rank pair lists (counts first, then ONE padded all_gather of the packed rows)."""
+    packed = torch.stack([(pair_hi.to(torch.int64) << 32) | pair_lo_global.to(torch.int64), score.contiguous().view(torch.int64)], 1)
+    parts = gather_varlen(packed, group)
+    return [((q[:, 0] >> 32).to(torch.int32), (q[:, 0] & 0xFFFFFFFF).to(torch.int32), q[:, 1].contiguous().view(torch.float64))
+            for q in parts]
+
+
+def match_threshold_sharded(hi_set, lo_shard_set, cc, lo_index_base, group=None, impl=None, local=None):
+    """All pairs (i, j) with cosine(hi_i, lo_j) > cc over the WHOLE lo set, of which this rank holds the shard starting at
+    global row ``lo_index_base`` (shards ascending with the rank).  Every rank returns the same (hi, lo_global, score) in
+    np.where's row-major order (mad/MaD.py:420-424).  ``local`` = precomputed (hi, lo_local, score) of this shard."""
+    if local is None:
+        from . import pipeline as P
+        local = P.match_threshold(hi_set, lo_shard_set, cc, impl=impl)
+    ph, pl, sc = local
+    pl = pl + int(lo_index_base)
+    if _world(group) == 1:
+        return ph, pl, sc
+    return merge_pair_lists(gather_pair_lists(ph, pl, sc, group))
+
+
+def collect_units(local_tables, n_units, group=None, like=None):
+    """Result collection of the batch path (map i -> rank i mod G, ``assign_units``): ``local_tables`` = this rank's
+    per-unit tensors [rows_u, ...] in its unit order; returns the ``n_units`` tables in unit order on every rank
+    (one all-gather of the row counts, one padded all-gather of the concatenated rows).  A rank that owns no unit
+    passes ``like`` = any tensor with the tables' dtype, device and row shape."""
+    g = _world(group)
+    if g == 1:
+        return list(local_tables)
+    rank = dist.get_rank(group)
+    if not local_tables and like is None:
+        raise ValueError("collect_units: a rank without units needs `like` to fix dtype and row shape")
+    like = local_tables[0] if local_tables else like
+    dev = like.device
+    per_rank = (int(n_units) + g - 1) // g
+    counts = torch.zeros(per_rank, dtype=torch.int64, device=dev)
+    for j, t in enumerate(local_tables):
+        counts[j] = t.shape[0]
+    all_counts = [torch.empty_like(counts) for _ in range(g)]
+    dist.all_gather(all_counts, counts, group=group)
+    rows = torch.cat(list(local_tables)) if local_tables else like[:0]
+    parts = gather_varlen(rows, group)
+    out = [None] * int(n_units)
+    for r in range(g):
+        offs = 0
+        for j, u in enumerate(assign_units(n_units, r, g)):
+            c = int(all_counts[r][j])
+            out[u] = parts[r][offs:offs + c]
+            offs += c
+    assert all(o is not None for o in out) and len(local_tables) == len(assign_units(n_units, rank, g))
+    return out

@@ -62,7 +62,14 @@ def _worker(rank, world, port, q):
         ok_var = [tuple(p.shape) for p in parts] == [(r + 2, 3) for r in range(world)] and \
             all(int(p[0, 0]) == r for r, p in enumerate(parts))
         units = par.assign_units(7, rank, world)
-        q.put((rank, ok_topk, ok_var, units))
+        # threshold mode sharded on the lo axis: per-shard pair lists from the oracle, gathered + merged == unsharded
+        lp, lsc = mo.match_threshold(hi, lo[s:e], 0.3)
+        got = par.match_threshold_sharded(None, None, 0.3, s, local=(torch.from_numpy(lp[:, 0].copy()),
+                                                                     torch.from_numpy(lp[:, 1].copy()), torch.from_numpy(lsc)))
+        op, osc2 = mo.match_threshold(hi, lo, 0.3)
+        ok_thr = bool(len(op) > 50 and np.array_equal(np.stack([got[0].numpy(), got[1].numpy()], 1), op)
+                      and np.abs(got[2].numpy() - osc2).max() < 1e-14)
+        q.put((rank, ok_topk, ok_var, units, ok_thr))
     finally:
         dist.destroy_process_group()
 
@@ -95,3 +102,4 @@ def test_world_size_2_gloo_topk_merge_and_varlen_gather():
     assert all(r[1] for r in res), "sharded + merged top-k differs from the unsharded oracle"
     assert all(r[2] for r in res), "variable-length gather returned wrong shapes / contents"
     assert res[0][3] == [0, 2, 4, 6] and res[1][3] == [1, 3, 5]
+    assert all(r[4] for r in res), "sharded threshold pair lists, gathered and merged, differ from the unsharded oracle"
