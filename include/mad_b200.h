@@ -143,6 +143,17 @@ int mad_log_gauss(const float* grid, int nx, int ny, int nz,
 /* ---- a4: gradient field (np.gradient, mad/MapSpace.py:187) ---------------------------------- */
 /* grad4[x][y][z] = (d/dx, d/dy, d/dz, 0): central differences, one-sided at the two ends. */
 int mad_gradient(const float* gauss, int nx, int ny, int nz, float* grad4, void* stream);
+/* Masked form of the same field.  Orientator / Descriptor read grad_list only inside a box around each keypoint
+ * (mad/Orientator.py:129-155: +-2r up-octave voxels, +-r base; mad/Descriptor.py:123-149: the rotated lattice,
+ * +-(2r - 1) sqrt(3) and +-(r - 0.5) sqrt(3)), so the field is computed on the 8x8x8 tiles those boxes touch.
+ * flags[mad_gradient_tiles(nx, ny, nz)] (device, zero-initialised by the caller): 0 = not needed, 1 = requested,
+ * 2 = computed.  mad_gradient_mark requests the tiles within reach_oct{0,1} voxels of every keypoint's (moved) voxel in
+ * its octave; mad_gradient_masked computes the requested tiles (values identical to mad_gradient) and marks them 2.
+ * Tiles never requested keep whatever grad4 held.  mad_gradient_mark(all tiles) == mad_gradient. */
+size_t mad_gradient_tiles(int nx, int ny, int nz);
+int mad_gradient_mark(const MadKeypoint* kp, int n_kp, const int* dims_oct_host, int reach_oct0, int reach_oct1,
+                      uint8_t* flags_oct0, uint8_t* flags_oct1, void* stream);
+int mad_gradient_masked(const float* gauss, int nx, int ny, int nz, float* grad4, uint8_t* flags, void* stream);
 
 /* ---- a5/a6: keypoint detection + sub-voxel refinement --------------------------------------- */
 /* peak_local_max(grid, exclude_border=border, threshold_abs=threshold) + check_localize

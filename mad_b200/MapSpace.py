@@ -112,7 +112,7 @@ class MapSpace(object):
                                       "MaD.run uses, mad/MaD.py:359)")
         self.voxelsp_list = [self.voxelsp / 2, self.voxelsp]
         self.space = _P.build_space(grid, self.map_padding, self.sig_init, self.sig_presmooth,
-                                    exact_f64=self.exact_f64, keep_gauss=True)
+                                    exact_f64=self.exact_f64, keep_gauss=True, full_gradient=False)
         self._cache = {}
 
     # ---- NumPy views of the device arrays (lazy) ------------------------------------------------
@@ -138,6 +138,8 @@ class MapSpace(object):
 
     @property
     def grad_list(self):
+        if "grad_list" not in self._cache:
+            _P.full_gradient(self.space)                        # tiles the stages have not asked for yet
         return self._host("grad_list", self.space.grad4, lambda a: a[..., :3])
 
     @property

@@ -71,6 +71,9 @@ SIGNATURES = {
     "mad_log_gauss_workspace_bytes": (_SZ, [_I, _I, _I]),
     "mad_log_gauss": (_I, [_P, _I, _I, _I, _P, _P, _I, C.c_float, _P, _P, _P, _SZ, _I, _P]),
     "mad_gradient": (_I, [_P, _I, _I, _I, _P, _P]),
+    "mad_gradient_tiles": (_SZ, [_I, _I, _I]),
+    "mad_gradient_mark": (_I, [_P, _I, _P, _I, _I, _P, _P, _P]),
+    "mad_gradient_masked": (_I, [_P, _I, _I, _I, _P, _P, _P]),
     "mad_detect": (_I, [_P, _I, _I, _I, _I, _I, C.c_float, _P, _I, _P, _P]),
     "mad_sort_keypoints_workspace_bytes": (_SZ, [_I]),
     "mad_sort_keypoints": (_I, [_P, _I, _P, _P, _P, _P, _SZ, _P]),

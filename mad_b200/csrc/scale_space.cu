@@ -1026,6 +1026,72 @@ gradient_kernel(const float* __restrict__ f, int nx, int ny, int nz, float4* __r
     }
 }
 
+// Masked form: the orientation / description stages only ever read the gradient inside a box around each keypoint
+// (+-2r voxels for the orientation patch, +-(2r-1) sqrt(3) for the rotated lattice; half of that in the base octave), so
+// the field is computed on the 8 x 8 x 8 tiles those boxes touch and nowhere else.  flags[tile]: 0 = not needed,
+// 1 = requested (computed by the next launch), 2 = computed.  The values written are the same as gradient_kernel's.
+constexpr int kTile = 8;
+static_assert(kTile == kGradSlab, "a gradient slab is one tile thick");
+
+__global__ void __launch_bounds__(256)
+gradient_masked_kernel(const float* __restrict__ f, int nx, int ny, int nz, float4* __restrict__ grad,
+                       const uint8_t* __restrict__ flags, int ty, int tz) {
+    const unsigned plane = (unsigned)ny * (unsigned)nz;
+    const unsigned p = blockIdx.x * 256u + threadIdx.x;
+    if (p >= plane) return;
+    const int y = (int)(p / (unsigned)nz);
+    const int z = (int)(p - (unsigned)y * (unsigned)nz);
+    if (flags[((size_t)blockIdx.y * ty + (y >> 3)) * tz + (z >> 3)] != 1) return;
+    const int x0 = blockIdx.y * kGradSlab;
+    const int x1 = min(nx, x0 + kGradSlab);
+    const long long sx = plane;
+    long long c = (long long)x0 * sx + p;
+    float prev = (x0 > 0) ? __ldg(f + c - sx) : 0.f;
+    float cur = __ldg(f + c);
+#pragma unroll 4
+    for (int x = x0; x < x1; ++x, c += sx) {
+        const float next = (x + 1 < nx) ? __ldg(f + c + sx) : 0.f;
+        float4 v;
+        if (x == 0) v.x = __fsub_rn(next, cur);
+        else if (x == nx - 1) v.x = __fsub_rn(cur, prev);
+        else v.x = __fmul_rn(__fsub_rn(next, prev), 0.5f);
+        v.y = grad_axis(f, c, y, ny, nz);
+        v.z = grad_axis(f, c, z, nz, 1);
+        v.w = 0.f;
+        grad[c] = v;
+        prev = cur;
+        cur = next;
+    }
+}
+
+__global__ void gradient_flags_done_kernel(uint8_t* __restrict__ flags, size_t n) {
+    const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+    if (i < n && flags[i] == 1) flags[i] = 2;
+}
+
+// One CTA per keypoint: requests every tile its box [vox - reach, vox + reach] touches (clipped to the grid).
+__global__ void gradient_mark_kernel(const MadKeypoint* __restrict__ kp, int n_kp, int nx0, int ny0, int nz0, int nx1,
+                                     int ny1, int nz1, int reach0, int reach1, uint8_t* __restrict__ flags0,
+                                     uint8_t* __restrict__ flags1) {
+    const MadKeypoint K = kp[blockIdx.x];
+    const int o = K.oct ? 1 : 0;
+    const int nx = o ? nx1 : nx0, ny = o ? ny1 : ny0, nz = o ? nz1 : nz0;
+    const int reach = o ? reach1 : reach0;
+    uint8_t* __restrict__ flags = o ? flags1 : flags0;
+    const int ty = (ny + kTile - 1) / kTile, tz = (nz + kTile - 1) / kTile;
+    const int ax = max(K.vox[0] - reach, 0) / kTile, bx = min(K.vox[0] + reach, nx - 1) / kTile;
+    const int ay = max(K.vox[1] - reach, 0) / kTile, by = min(K.vox[1] + reach, ny - 1) / kTile;
+    const int az = max(K.vox[2] - reach, 0) / kTile, bz = min(K.vox[2] + reach, nz - 1) / kTile;
+    const int wy = by - ay + 1, wz = bz - az + 1;
+    const int total = (bx - ax + 1) * wy * wz;
+    for (int t = threadIdx.x; t < total; t += blockDim.x) {
+        const int k = t % wz, j = (t / wz) % wy, i = t / (wz * wy);
+        uint8_t* fl = flags + ((size_t)(ax + i) * ty + (ay + j)) * tz + (az + k);
+        if (*fl == 0) *fl = 1;                                    // benign race: every writer stores 1
+    }
+    (void)n_kp;
+}
+
 extern "C" int mad_gradient(const float* gauss, int nx, int ny, int nz, float* grad4, void* stream) {
     MAD_CHECK_ARG(gauss && grad4 && nx >= 2 && ny >= 2 && nz >= 2);
     MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad4) & 15) == 0);
@@ -1033,6 +1099,42 @@ extern "C" int mad_gradient(const float* gauss, int nx, int ny, int nz, float* g
     dim3 grid_dim((unsigned)mad_ceil_div((long long)ny * nz, 256), (unsigned)mad_ceil_div(nx, kGradSlab));
     MAD_PROF("gradient_kernel", stream);
     gradient_kernel<<<grid_dim, 256, 0, (cudaStream_t)stream>>>(gauss, nx, ny, nz, reinterpret_cast<float4*>(grad4));
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}
+
+extern "C" size_t mad_gradient_tiles(int nx, int ny, int nz) {
+    return (size_t)mad_ceil_div(nx, kTile) * (size_t)mad_ceil_div(ny, kTile) * (size_t)mad_ceil_div(nz, kTile);
+}
+
+extern "C" int mad_gradient_mark(const MadKeypoint* kp, int n_kp, const int* dims_oct_host, int reach_oct0, int reach_oct1,
+                                 uint8_t* flags_oct0, uint8_t* flags_oct1, void* stream) {
+    MAD_CHECK_ARG(dims_oct_host && n_kp >= 0 && reach_oct0 >= 0 && reach_oct1 >= 0);
+    if (n_kp == 0) return MAD_OK;
+    MAD_CHECK_ARG(kp && flags_oct0 && flags_oct1);
+    const int* d = dims_oct_host;
+    MAD_PROF("gradient_mark_kernel", stream);
+    gradient_mark_kernel<<<n_kp, 128, 0, (cudaStream_t)stream>>>(kp, n_kp, d[0], d[1], d[2], d[3], d[4], d[5], reach_oct0,
+                                                               reach_oct1, flags_oct0, flags_oct1);
+    MAD_LAUNCH_OK();
+    return MAD_OK;
+}
+
+extern "C" int mad_gradient_masked(const float* gauss, int nx, int ny, int nz, float* grad4, uint8_t* flags, void* stream) {
+    MAD_CHECK_ARG(gauss && grad4 && flags && nx >= 2 && ny >= 2 && nz >= 2);
+    MAD_CHECK_ARG((reinterpret_cast<uintptr_t>(grad4) & 15) == 0);
+    MAD_CHECK_ARG(nx <= 65535 * kTile && (long long)ny * nz < (1LL << 31));
+    const int ty = (int)mad_ceil_div(ny, kTile), tz = (int)mad_ceil_div(nz, kTile);
+    dim3 grid_dim((unsigned)mad_ceil_div((long long)ny * nz, 256), (unsigned)mad_ceil_div(nx, kGradSlab));
+    {
+        MAD_PROF("gradient_masked_kernel", stream);
+        gradient_masked_kernel<<<grid_dim, 256, 0, (cudaStream_t)stream>>>(gauss, nx, ny, nz, reinterpret_cast<float4*>(grad4),
+                                                                         flags, ty, tz);
+        MAD_LAUNCH_OK();
+    }
+    const size_t n = mad_gradient_tiles(nx, ny, nz);
+    MAD_PROF("gradient_flags_done_kernel", stream);
+    gradient_flags_done_kernel<<<(unsigned)mad_ceil_div((long long)n, 256), 256, 0, (cudaStream_t)stream>>>(flags, n);
     MAD_LAUNCH_OK();
     return MAD_OK;
 }

@@ -11,6 +11,7 @@ The reference-shaped classes (MapSpace, Detector, Orientator, Descriptor) are th
 these functions.  Nothing here computes on the CPU: without a CUDA device every call raises.
 """
 import ctypes as C
+import math
 import os
 
 import numpy as np
@@ -141,16 +142,61 @@ class Space(object):
         self.logs = []       # map_space            f32
         self.gauss = []      # gauss_list           f32
         self.grad4 = []      # grad_list as float4  f32 [x][y][z][4]
+        self.grad_flags = [] # per octave: None = the whole field is computed; else uint8 tile flags (mad_gradient_masked)
         self.dims = []
         self.n_input_voxels = 0
+        self._gauss = []     # Gaussian grids kept while tiles of the gradient may still be requested
+        self._grad_done = {}  # (id(keypoint table object), radius) -> that object (kept alive: ids stay unique)
 
     @property
     def dims_host(self):
         return np.array([d for o in self.dims for d in o], dtype=np.int32)
 
 
-def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True, keep_gauss=True):
-    """a1-a4.  ``grid``: float32 [x][y][z], torch CUDA tensor or NumPy array (copied to the device)."""
+def gradient_reach(radius):
+    """Voxels around a keypoint's voxel the orientation / description stages may read, (up octave, base octave):
+    the orientation patch spans +-2r (+-r) voxels (mad/Orientator.py:129-155), the rotated description lattice
+    +-(2r - 1) sqrt(3) (+-(r - 0.5) sqrt(3)) before the nearest-voxel rule (mad/Descriptor.py:123-149)."""
+    up = max(2 * radius, int(math.ceil((2 * radius - 1) * math.sqrt(3.0))) + 1)
+    base = max(radius, int(math.ceil((radius - 0.5) * math.sqrt(3.0))) + 1)
+    return up, base
+
+
+def ensure_gradient(space, kp, radius=8):
+    """Computes the gradient tiles within reach of the keypoints ``kp`` (no-op for a fully computed field)."""
+    if all(f is None for f in space.grad_flags) or len(kp) == 0:
+        return
+    key = (id(kp), int(radius))
+    if key in space._grad_done:
+        return
+    st = _stream()
+    up, base = gradient_reach(int(radius))
+    f0, f1 = space.grad_flags
+    if f0 is None or f1 is None:
+        raise _lib.MadError("ensure_gradient: octaves must share the gradient mode")
+    call("mad_gradient_mark", _ptr(kp.table), len(kp), _dptr(space.dims_host), up, base, _ptr(f0), _ptr(f1), st)
+    for o, (gx, gy, gz) in enumerate(space.dims):
+        call("mad_gradient_masked", _ptr(space._gauss[o]), gx, gy, gz, _ptr(space.grad4[o]), _ptr(space.grad_flags[o]), st)
+    space._grad_done[key] = kp
+
+
+def full_gradient(space):
+    """Materialises the whole gradient field (``MapSpace.grad_list``): every tile not computed yet is requested."""
+    st = _stream()
+    for o, (gx, gy, gz) in enumerate(space.dims):
+        fl = space.grad_flags[o]
+        if fl is None:
+            continue
+        fl[fl == 0] = 1
+        call("mad_gradient_masked", _ptr(space._gauss[o]), gx, gy, gz, _ptr(space.grad4[o]), _ptr(fl), st)
+        space.grad_flags[o] = None
+    return space.grad4
+
+
+def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True, keep_gauss=True, full_gradient=True):
+    """a1-a4.  ``grid``: float32 [x][y][z], torch CUDA tensor or NumPy array (copied to the device).
+    full_gradient=False: the gradient field is computed later, only on the tiles the keypoints' patches touch
+    (``ensure_gradient``, called by ``orient`` / ``describe``) or on demand (``full_gradient``)."""
     _require_cuda()
     if isinstance(grid, np.ndarray):
         grid = torch.from_numpy(np.ascontiguousarray(grid, dtype=np.float32)).cuda()
@@ -195,10 +241,17 @@ def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True
              _ptr(ws), ws_bytes, 1 if exact_f64 else 0, st)
         del ws
         gr = torch.empty((gx, gy, gz, 4), dtype=torch.float32, device=dev)
-        call("mad_gradient", _ptr(gs), gx, gy, gz, _ptr(gr), st)
+        if full_gradient:
+            call("mad_gradient", _ptr(gs), gx, gy, gz, _ptr(gr), st)
+            sp.grad_flags.append(None)
+        else:
+            sp.grad_flags.append(torch.zeros(_lib.lib.mad_gradient_tiles(gx, gy, gz), dtype=torch.uint8, device=dev))
+        sp._gauss.append(gs)
         sp.logs.append(lg)
         sp.gauss.append(gs if keep_gauss else None)
         sp.grad4.append(gr)
+    if full_gradient and not keep_gauss:
+        sp._gauss = []
     return sp
 
 
@@ -285,6 +338,7 @@ def orient(space, kp, radius=8, lim_main=6, lim_sec=6):
     n = len(kp)
     if n == 0:
         return Oriented(torch.empty((1, 2), dtype=torch.int32, device=dev), 0)
+    ensure_gradient(space, kp, radius)
     n_ori = torch.empty(n, dtype=torch.int32, device=dev)
     slots = torch.empty((n, MAX_ORI), dtype=torch.int32, device=dev)
     dims = space.dims_host
@@ -309,6 +363,7 @@ def describe(space, kp, ori, radius=8):
     dsc = torch.empty((d, DSC_LEN), dtype=torch.int16, device=dev)
     if d == 0:
         return dsc
+    ensure_gradient(space, kp, radius)
     dims = space.dims_host
     call("mad_describe", _ptr(space.grad4[0]), _ptr(space.grad4[1]), _dptr(dims), _ptr(kp.table), _ptr(ori.table), d,
          int(radius), C.byref(tb.z_dsc), _ptr(tb.rf), _ptr(tb.rf_inv), tb.ori_zones, _ptr(dsc), st)
@@ -316,10 +371,15 @@ def describe(space, kp, ori, radius=8):
 
 
 def describe_struct(grid, patch_size=16, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True,
-                    keep_gauss=False):
-    """The whole a1-a12 chain of ``MaD._describe_struct`` (mad/MaD.py:358-368) on device arrays."""
+                    keep_gauss=False, full_gradient=None):
+    """The whole a1-a12 chain of ``MaD._describe_struct`` (mad/MaD.py:358-368) on device arrays.
+    full_gradient: None = only when the dense arrays are kept for inspection (keep_gauss); the product path computes
+    the gradient on the tiles around the keypoints (same descriptors, see ``ensure_gradient``)."""
     r = (patch_size - patch_size % 2) // 2
-    sp = build_space(grid, map_padding, sig_init, sig_presmooth, exact_f64=exact_f64, keep_gauss=keep_gauss)
+    if full_gradient is None:
+        full_gradient = bool(keep_gauss)
+    sp = build_space(grid, map_padding, sig_init, sig_presmooth, exact_f64=exact_f64, keep_gauss=keep_gauss,
+                     full_gradient=full_gradient)
     kp = detect(sp)
     ori = orient(sp, kp, r)
     dsc = describe(sp, kp, ori, r)

@@ -4,6 +4,7 @@ Runs only in the build container (needs /root/reference; same shims / scratch di
 The inputs are the ones bench.py times (oracle/synth.py: c2_inputs, c4_snapshot, c5_descriptor_sets):
 
     python oracle/gen_golden_bench.py c2map          # C2 assembly map 256^3          -> tests/golden/c2.npz
+    python oracle/gen_golden_bench.py c2planes       # + per-x-plane CRC32 of the dense arrays (re-runs build_space only)
     python oracle/gen_golden_bench.py c2comp 0 1 2   # C2 component maps (any subset)  -> /tmp parts
     python oracle/gen_golden_bench.py c2pairs        # merge parts + hi_all x lo pairs -> tests/golden/c2_comp.npz
     python oracle/gen_golden_bench.py c4 0 31 63     # three of the 64 C4 snapshots    -> tests/golden/c4.npz
@@ -40,6 +41,17 @@ def run_map(tag, grid, voxelsp):
     return out, dsc
 
 
+def plane_crcs(a):
+    """CRC32 of every x plane of a dense array after flushing |v| < 1e-10 (tests/helpers.py:plane_crcs is the twin)."""
+    a = np.ascontiguousarray(a)
+    out = np.zeros(a.shape[0], dtype=np.uint32)
+    for x in range(a.shape[0]):
+        p = a[x].copy()
+        p[np.abs(p) < G.FLUSH] = 0
+        out[x] = zlib.crc32(p.tobytes())
+    return out
+
+
 def unit_rows(d):
     """mad/MaD.py:416-419 (zero rows stay zero)."""
     d = d.astype(np.float64)
@@ -59,6 +71,28 @@ def main(argv):
         out, dsc = run_map("c2map", grid, synth.C2["voxelsp"])
         np.save(os.path.join(PARTS, "c2map_dsc.npy"), dsc)
         np.savez_compressed(os.path.join(G.GOLD, "c2.npz"), **out)
+    elif what == "c2planes":
+        # At 1.6e8 values per array a float64 rounding difference (LAPACK gbsv vs a streaming Thomas recurrence, FMA vs
+        # mul + add) is expected to flip the float32 rounding of a handful of values, so a whole-array SHA-256 is too
+        # brittle at this size: per-x-plane CRC32s of the flushed arrays localise and count the differing planes.
+        from mad.MapSpace import MapSpace
+        grid, _ = synth.c2_inputs(0)
+        mrc = os.path.join(G.WORK, "c2map.mrc")
+        ref_shims.write_mrc_stub(mrc, np.ascontiguousarray(grid, dtype=np.float32), synth.C2["voxelsp"], (0.0, 0.0, 0.0))
+        ms = MapSpace(mrc)
+        ms.build_space()
+        path = os.path.join(G.GOLD, "c2.npz")
+        with np.load(path, allow_pickle=False) as z:
+            out = {k: z[k] for k in z.files}
+        arrays = {"up_grid": ms.grid_list[0]}
+        for o in range(2):
+            arrays["log%d" % o], arrays["gauss%d" % o], arrays["grad%d" % o] = ms.map_space[o], ms.gauss_list[o], ms.grad_list[o]
+        for k, a in arrays.items():
+            assert G.sha_flushed(a) == str(out[k + "_sha256_flushed"]), k
+            out[k + "_plane_crc32_flushed"] = plane_crcs(a)
+        np.savez_compressed(path, **out)
+        np.save(os.path.join(PARTS, "c2_up_grid.npy"), ms.grid_list[0])
+        print("added plane CRCs to c2.npz")
     elif what == "c2comp":
         _, comps = synth.c2_inputs(0)
         for i in [int(a) for a in argv[1:]]:

@@ -38,6 +38,15 @@ def equal_flushed(a, b):
     return np.array_equal(flushed(a), flushed(b))
 
 
+def plane_crcs(a):
+    """CRC32 of every x plane after flushing |v| < FLUSH (twin of oracle/gen_golden_bench.py:plane_crcs)."""
+    a = np.ascontiguousarray(a)
+    out = np.zeros(a.shape[0], dtype=np.uint32)
+    for x in range(a.shape[0]):
+        out[x] = zlib.crc32(flushed(a[x]).tobytes())
+    return out
+
+
 def crc_rows(dsc):
     return np.array([zlib.crc32(np.ascontiguousarray(r).tobytes()) for r in dsc], dtype=np.uint32)
 

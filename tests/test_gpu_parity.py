@@ -100,6 +100,30 @@ def test_orientations_and_descriptors_equal_reference(P, case):
     assert H.sha(d) == str(g["dsc_sha256"])
 
 
+@pytest.mark.parametrize("case", ["tiny", "small", "pair_lo", "c1"])
+def test_masked_gradient_path_equals_full_field_path(P, case):
+    """The product path computes the gradient only on the 8^3 tiles around the keypoints (mad_gradient_mark /
+    mad_gradient_masked): same keypoints, orientations and descriptors as with the whole field, the computed tiles hold
+    the reference's values, and ``full_gradient`` afterwards completes the field bit for bit."""
+    import synth
+    g, sp, kp, ori, dsc = run_case(P, case)
+    grid = synth.dequantise_u16(g["input_q"])
+    sp2, kp2, ori2, dsc2 = P.describe_struct(grid)
+    assert sp2.grad_flags[0] is not None and sp.grad_flags[0] is None
+    assert torch.equal(kp.table[:len(kp)], kp2.table[:len(kp2)]) and torch.equal(ori.table[:len(ori)], ori2.table[:len(ori2)])
+    assert torch.equal(dsc, dsc2)
+    for o in range(2):
+        fl = sp2.grad_flags[o].clone()
+        assert int((fl == 1).sum()) == 0 and int((fl == 2).sum()) > 0
+        nx, ny, nz = sp2.dims[o]
+        t = fl.view((nx + 7) // 8, (ny + 7) // 8, (nz + 7) // 8)
+        done = t.repeat_interleave(8, 0).repeat_interleave(8, 1).repeat_interleave(8, 2)[:nx, :ny, :nz] == 2
+        assert torch.equal(sp2.grad4[o][done], sp.grad4[o][done])
+    P.full_gradient(sp2)
+    for o in range(2):
+        assert sp2.grad_flags[o] is None and torch.equal(sp2.grad4[o], sp.grad4[o])
+
+
 def test_stages_against_oracle_inputs(P):
     """Stage isolation: orient/describe fed with the ORACLE's keypoints reproduce the oracle."""
     grid, osp, okp, oori, odsc, tab_o = H.oracle_case("small")
