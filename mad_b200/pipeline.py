@@ -679,6 +679,69 @@ class MapStream(object):
         return out
 
 
+class MapBatch(object):
+    """A batch of independent maps (ensemble frames / conformational snapshots: the loops of mad/MaD.py:143-162,178-189)
+    through a1-a12.  Small maps are launch- and host-latency bound (a 96^3 map is ~40 launches and 3 count read-backs for
+    under a millisecond of GPU work), so ``streams`` host threads, each with its own CUDA stream, persistent upload buffer
+    and pinned result stage, work on different maps: one map's host round trips hide behind another map's kernels.
+
+        batch = MapBatch(streams=4)
+        results = batch.run(list_of_pinned_grids)          # [{"n_kp", "n_dsc", "dsc", "kp", "ori"}] in input order
+    """
+
+    def __init__(self, streams=4, patch_size=16, exact_f64=True):
+        _require_cuda()
+        from concurrent.futures import ThreadPoolExecutor
+        self.nw = max(1, int(streams))
+        self.patch, self.exact = patch_size, exact_f64
+        self.device = torch.cuda.current_device()
+        self.streams = [torch.cuda.Stream() for _ in range(self.nw)]
+        self.stages = [HostStage() for _ in range(self.nw)]
+        self.up = [None] * self.nw
+        self.pool = ThreadPoolExecutor(self.nw)
+        self.last_d2h_bytes = 0
+        device_tables(torch.device("cuda", self.device))       # one-time table initialisation before the workers start
+
+    def _work(self, w, grids, download):
+        torch.cuda.set_device(self.device)
+        out = []
+        with torch.cuda.stream(self.streams[w]):
+            for j in range(w, len(grids), self.nw):
+                g = grids[j]
+                if isinstance(g, np.ndarray):
+                    g = torch.from_numpy(np.ascontiguousarray(g, dtype=np.float32))
+                if not g.is_cuda:                               # persistent upload buffer: no allocator traffic per map
+                    if self.up[w] is None or self.up[w].shape != g.shape:
+                        self.up[w] = torch.empty(tuple(g.shape), dtype=torch.float32, device="cuda")
+                    self.up[w].copy_(g, non_blocking=True)
+                    g = self.up[w]
+                sp, kp, ori, dsc = describe_struct(g, patch_size=self.patch, exact_f64=self.exact)
+                r = {"n_kp": len(kp), "n_dsc": len(ori)}
+                if download:
+                    st = self.stages[w]
+                    r.update(dsc=st.fetch("dsc%d" % j, dsc), kp=st.fetch("kp%d" % j, kp.table[:len(kp)]),
+                             ori=st.fetch("ori%d" % j, ori.table[:len(ori)]))
+                else:
+                    r.update(dsc=dsc, kp=kp.table[:len(kp)], ori=ori.table[:len(ori)])
+                out.append((j, r))
+            self.streams[w].synchronize()
+        return out
+
+    def run(self, grids, download=True):
+        """``grids``: float32 [x][y][z] maps -- pinned CPU tensors / NumPy arrays are uploaded, CUDA tensors used in place.
+        download=True: tables come back as host arrays (views of pinned buffers, valid until the next ``run``)."""
+        main = torch.cuda.current_stream()
+        for s_ in self.streams:
+            s_.wait_stream(main)
+        parts = [f.result() for f in [self.pool.submit(self._work, w, grids, download) for w in range(self.nw)]]
+        for s_ in self.streams:
+            main.wait_stream(s_)
+        res = [r for _, r in sorted((x for p in parts for x in p), key=lambda x: x[0])]
+        if download:
+            self.last_d2h_bytes = int(sum(r[k].numel() * r[k].element_size() for r in res for k in ("dsc", "kp", "ori")))
+        return res
+
+
 def concat_sets(sets):
     """One DescriptorSet holding the rows of several (e.g. all subunits of an assembly) + row offsets,
     so that one matching launch serves them all; pairs come back with global hi rows."""
