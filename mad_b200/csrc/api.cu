@@ -179,12 +179,15 @@ extern "C" int mad_match_fill(const MadDscSet* hi, const MadDscSet* lo, double c
 
 // Partial top-k lists a kernel writes per hi row: the uint8 kernel has two epilogue groups per
 // segment, each with its own list.
-static int topk_lists(int M, int N, int impl) {
-    return impl == 0 ? 2 * mad_match_u8_segments_topk(M, N) : mad_match_segments(M, N, impl);
+// k <= 8: three lists per segment (the drain warps' list + the two epilogue groups' lists of the sweep's first tiles);
+// k > 8: one per (segment, group)
+static int u8_lists_per_segment(int k) { return k <= 8 ? 3 : 2; }
+static int topk_lists(int M, int N, int k, int impl) {
+    return impl == 0 ? u8_lists_per_segment(k) * mad_match_u8_segments_topk(M, N) : mad_match_segments(M, N, impl);
 }
 
 extern "C" size_t mad_match_topk_workspace_bytes(int M, int N, int k, int impl) {
-    const int S = topk_lists(M, N, impl);
+    const int S = topk_lists(M, N, k, impl);
     if (S <= 1 || M <= 0) return 256;
     return mad_align_up((size_t)S * M * k * sizeof(int32_t), 256) + mad_align_up((size_t)S * M * k * sizeof(double), 256);
 }
@@ -203,9 +206,9 @@ extern "C" int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, i
         // -inf as float64 = 0xFFF0000000000000: written by the merge kernel over zero shards
         return mad_topk_merge_launch(topk_idx, topk_score, 0, M, k, topk_idx, topk_score, st);
     }
-    const int S = topk_lists(M, lo->rows, impl);                   // lists to merge
+    const int S = topk_lists(M, lo->rows, k, impl);                // lists to merge
     auto run_topk = [&](int lists, int32_t* oi, double* os) {
-        const int segs = impl == 0 ? lists / 2 : lists;
+        const int segs = impl == 0 ? lists / u8_lists_per_segment(k) : lists;
         if (impl == 0)
             return mad_match_u8_topk(hi->u8, hi->rows, hi->rows_padded, lo->u8, lo->rows, lo->rows_padded, hi->norm2,
                                      lo->norm2, lo->rnorm, segs, k, lo_index_base, oi, os, st);

@@ -78,6 +78,65 @@ __device__ __forceinline__ void mad_top8i_insert(int (&td)[8], int (&tn)[8], int
     bi[0] = c[0] ? id : bi[0];
 }
 
+// The same list with a float32 image of every entry's score (relative error < 1e-6): the order of two entries is decided on
+// the images whenever they differ by more than 4e-6 of the larger one, and on the exact integer ratios otherwise -- the same
+// order as mad_top8i_insert's at a fraction of the instructions (the 128-bit products are needed for near-ties only).
+// (out of line: it runs for near-ties only and must not bloat its callers -- the matcher's warps share one instruction cache)
+static __device__ __noinline__ bool mad_ratio_before_nl(int d, int n, int id, int pd, int pn, int pi) {
+    return mad_ratio_before(d, n, id, pd, pn, pi);
+}
+__device__ __forceinline__ bool mad_score32_before(float s, int d, int n, int id, float ps, int pd, int pn, int pi) {
+    if (pi < 0) return true;
+    const float tol = 4e-6f * fmaxf(s, ps);
+    if (s > ps + tol) return true;
+    if (s < ps - tol) return false;
+    return mad_ratio_before_nl(d, n, id, pd, pn, pi);
+}
+
+// Called by ALL lanes of a warp (`active` = this lane has a candidate).  The eight position decisions are taken on the
+// images; only if some lane of the warp has an image within the tolerance of one of its entries does the warp redo the
+// decisions on the exact ratios (one warp-uniform branch: the 128-bit products stay off the common path).
+__device__ __forceinline__ void mad_top8f_insert(float (&ts)[8], int (&td)[8], int (&tn)[8], int (&bi)[8], bool active, float s,
+                                                 int d, int n, int id) {
+    bool c[8];
+    bool amb = false;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        const float ps = ts[q];
+        const bool empty = bi[q] < 0;
+        const float tol = 4e-6f * fmaxf(s, ps);
+        const bool gt = s > ps + tol, lt = s < ps - tol;
+        c[q] = active && (empty || gt);
+        amb |= active && !empty && !gt && !lt;
+    }
+    if (__any_sync(0xFFFFFFFFu, amb)) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) c[q] = active && mad_score32_before(s, d, n, id, ts[q], td[q], tn[q], bi[q]);
+    }
+#pragma unroll
+    for (int q = 7; q >= 1; --q) {
+        ts[q] = c[q - 1] ? ts[q - 1] : (c[q] ? s : ts[q]);
+        td[q] = c[q - 1] ? td[q - 1] : (c[q] ? d : td[q]);
+        tn[q] = c[q - 1] ? tn[q - 1] : (c[q] ? n : tn[q]);
+        bi[q] = c[q - 1] ? bi[q - 1] : (c[q] ? id : bi[q]);
+    }
+    ts[0] = c[0] ? s : ts[0];
+    td[0] = c[0] ? d : td[0];
+    tn[0] = c[0] ? n : tn[0];
+    bi[0] = c[0] ? id : bi[0];
+}
+
+// Release / acquire accesses to a shared-memory state word (CTA scope): the hand-off protocols below order their data
+// with these instead of __threadfence_block(), which compiles to the much heavier MEMBAR.SC.CTA.
+__device__ __forceinline__ void mad_st_release_cta(volatile int* p, int v) {
+    asm volatile("st.release.cta.shared::cta.s32 [%0], %1;" ::"r"((uint32_t)__cvta_generic_to_shared((const void*)p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ int mad_ld_acquire_cta(volatile int* p) {
+    int v;
+    asm volatile("ld.acquire.cta.shared::cta.s32 %0, [%1];" : "=r"(v) : "r"((uint32_t)__cvta_generic_to_shared((const void*)p)) : "memory");
+    return v;
+}
+
 // v[j] for a run-time j without spilling v to local memory: 5 levels of selects.
 __device__ __forceinline__ uint32_t mad_select32(const uint32_t (&v)[32], int j) {
     uint32_t a[16];

@@ -29,6 +29,8 @@
 #include <cuda.h>
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 #include "match_common.cuh"
 
@@ -45,7 +47,7 @@ constexpr int ACCS = 4;            // TMEM accumulator ring (4 x 128 columns)
 constexpr uint32_t KB_BYTES = BM * BKB;             // 16 KB: one k-block of 128 rows
 constexpr uint32_t A_BYTES = KBLOCKS * KB_BYTES;    // 128 KB resident hi tile
 constexpr int EPI_WARPS = 8;       // two epilogue groups of 4 warps (one per TMEM lane quadrant), alternating tiles
-constexpr int THREADS = 128 + 32 * EPI_WARPS;
+constexpr int THREADS = 128 + 32 * EPI_WARPS + 64;     // + warps 12, 13: two more drain warps of the top-8 mode (idle otherwise)
 constexpr uint32_t TMEM_COLS = 512;
 // count value a hand-off time-out leaves behind: the host raises instead of returning a truncated pair list
 constexpr unsigned long long MAD_MATCH_TIMEOUT_COUNT = 1ull << 62;
@@ -53,7 +55,16 @@ constexpr int STG = 96;            // staged candidates per epilogue warp
 constexpr size_t STG_BYTES = (size_t)EPI_WARPS * STG * (sizeof(unsigned long long) + sizeof(int));
 constexpr size_t RB_BYTES = (size_t)2 * 2 * 256 * sizeof(float);          // per epilogue group, double-buffered 1/|lo| of a tile
 // dynamic smem: [1024 slack][A 128K][B ring 80K][staging 9K][rnorm 8K][barriers, tmem slot, counters 512]
-constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + RB_BYTES + 512;
+constexpr size_t THR_BYTES = 512;   // TOP8: per-row list thresholds published by the drain warps
+// TOP8 staging: per epilogue warp 2 halves x 32 lanes x TOP_SLOTS self-contained 8-byte entries (in the pairs staging area)
+constexpr int TOP_SLOTS = 2;
+// TOP8: the first TOP_LOCAL_TILES tiles of a sweep are handled by the epilogue threads themselves (thread-local list, fresh
+// threshold): 60 % of a row's ~8 ln(N / 8) candidate events fall into them, and through the hand-off every one of those
+// would cost a round trip to a drain warp whose threshold lags.  Lists per (segment, row): drain, local group 0, local group 1.
+constexpr int TOP_LOCAL_TILES = 4;
+constexpr unsigned long long TOP_INVALID = ~0ull;
+static_assert((size_t)EPI_WARPS * 2 * 32 * TOP_SLOTS * sizeof(unsigned long long) <= STG_BYTES, "TOP8 slots fit the staging area");
+constexpr size_t SMEM_BYTES = 1024 + A_BYTES + (size_t)STAGES * KB_BYTES + STG_BYTES + RB_BYTES + 512 + THR_BYTES;
 static_assert(SMEM_BYTES <= 232448, "shared memory budget of one sm_100 CTA");
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -183,9 +194,14 @@ struct U8Args {
     unsigned long long* count;    // device counter (hits found, may exceed cap)
     // TOPK
     int k, lo_index_base;
+    int dbg;                      // MAD_TOPK_DBG (measurement only): 1 = drain consumes without inserting, 2 = epilogue stages nothing
     int32_t* topk_idx;            // [2 S][M][k]: one list per (segment, epilogue group)
     double* topk_score;
 };
+
+// measurement counters of the top-8 hand-off (MAD_TOPK_DBG & 32): epilogue round cycles, publish-wait cycles, publishes, rounds,
+// drain passes, drain busy cycles, entries inserted, entries dropped as stale
+__device__ unsigned long long g_top_dbg[8];
 
 enum { MODE_PAIRS = 0, MODE_TOPK = 1, MODE_TOP8 = 2 };   // TOP8: k <= 8, list in registers
 
@@ -226,6 +242,10 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     volatile int* s_half = reinterpret_cast<volatile int*>(gen + BAR_OFF + 8 * (2 * NSTAGE + 2 * ACCS + 2));
     volatile int* s_done = s_half + 2 * EPI_WARPS;
     static_assert(8 * (2 * STAGES + 2 * ACCS + 2) + 3 * EPI_WARPS * sizeof(int) <= 512, "misc shared region");
+    // TOP8 (k <= 8): the epilogue warps only STAGE candidates (lane l of epilogue warp e owns TOP_SLOTS slots per half), the
+    // two drain warps keep the per-row lists in registers and publish each row's threshold here
+    volatile unsigned long long* top_slots = reinterpret_cast<volatile unsigned long long*>(gen + STG_OFF);
+    volatile float* s_thr8 = reinterpret_cast<volatile float*>(gen + BAR_OFF + 512);             // [BM]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = (NCTA == 2) ? cluster_ctarank() : 0u;    // 0 = leader of the pair
@@ -249,7 +269,11 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
     // publishes its list's threshold here (the staging area is unused in top-k mode) and pre-filters with the larger of
     // the two -- the merged k-th best is at least that good, so nothing that could reach the merged list is skipped
     volatile float* s_thr = reinterpret_cast<volatile float*>(gen + STG_OFF);                  // [2 groups][BM]
-    if ((MODE == MODE_TOPK || MODE == MODE_TOP8) && threadIdx.x < 2 * BM) s_thr[threadIdx.x] = -1.f;
+    if (MODE == MODE_TOPK && threadIdx.x < 2 * BM) s_thr[threadIdx.x] = -1.f;
+    if (MODE == MODE_TOP8) {
+        for (int i = threadIdx.x; i < EPI_WARPS * 2 * 32 * TOP_SLOTS; i += THREADS) top_slots[i] = TOP_INVALID;
+        if (threadIdx.x < BM) s_thr8[threadIdx.x] = -1.f;
+    }
     if (NCTA == 2) cluster_sync_all();                             // barriers of both CTAs exist before any remote arrive
     if (warp == 2) {
         if (NCTA == 2) {
@@ -402,7 +426,93 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             }
             if (spins == (1LL << 27) - 1 && lane == 0) atomicExch(a.count, MAD_MATCH_TIMEOUT_COUNT);   // fail loudly on the host
         }
-    } else if (warp >= 4) {
+    } else if ((warp == 2 || warp == 3 || warp >= 4 + EPI_WARPS) && MODE == MODE_TOP8) {
+        // ===================== drain warps (TOP8): warps 2, 3, 12, 13 own the lists of one 32-row quadrant each ==========
+        // Lane l keeps the top-8 list of row 32 dq + l in registers: (float32 score image, dot, |lo|^2, index), ordered by the
+        // exact integer ratio dot^2 / |lo|^2 wherever the images are closer than 4e-6.  The epilogue warps of BOTH groups stage
+        // their candidates per lane (lane l of an epilogue warp of quadrant q owns row 32 q + l), so a published half is
+        // consumed by all 32 lanes at once: every lane inserts its own row's (at most TOP_SLOTS) entries -- no routing, no
+        // atomics, one list per row for both column halves of a tile.
+        // With the lists in the epilogue threads a warp paid ~300 cycles per candidate of ANY of its 32 rows on the critical
+        // path of its tile (140 candidate events per row at 100 000 columns: 1.3 M cycles against 1.6 M of MMA work).
+        const int dq = warp < 4 ? warp - 2 : warp - (4 + EPI_WARPS) + 2;
+        float ts[8];
+        int td[8], tn[8], bi[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { ts[i] = 0.f; td[i] = 0; tn[i] = 1; bi[i] = -1; }
+        const int row = m0 + 32 * dq + lane;
+        const int n2a_i = row < a.M ? __ldg(a.hi_n2 + row) : 0;
+        const float ra = n2a_i > 0 ? (float)(1.0 / sqrt((double)n2a_i)) : 0.f;
+        bool timeout = false;
+        for (long long spins = 0;; ++spins) {
+            if (spins >= (1LL << 26)) { timeout = true; break; }      // (bounded: a protocol error must not hang the device)
+            const int done = mad_ld_acquire_cta(&s_done[dq]) + mad_ld_acquire_cta(&s_done[4 + dq]);
+            bool any = false;
+#pragma unroll 1
+            for (int g = 0; g < 2; ++g) {
+                const int e = g * 4 + dq;                             // epilogue warp of group g, quadrant dq
+#pragma unroll 1
+                for (int h = 0; h < 2; ++h) {
+                    const int tt = mad_ld_acquire_cta(&s_half[2 * e + h]);      // (acquire: the entries were written before the state word)
+                    if (tt <= 0) continue;
+                    any = true;
+                    const long long dc0 = (a.dbg & 32) ? clock64() : 0;
+                    int n_ins = 0, n_stale = 0;
+                    volatile unsigned long long* sl = top_slots + ((e * 2 + h) * 32 + lane) * TOP_SLOTS;
+                    unsigned long long ent[TOP_SLOTS];
+#pragma unroll
+                    for (int u = 0; u < TOP_SLOTS; ++u) { ent[u] = sl[u]; sl[u] = TOP_INVALID; }
+                    __syncwarp();
+                    if (lane == 0) mad_st_release_cta(&s_half[2 * e + h], 0);                  // the half may be refilled
+                    const int colbase = a.lo_index_base + (tt - 1) * TN;
+                    bool changed = false;
+#pragma unroll
+                    for (int u = 0; u < TOP_SLOTS; ++u) {
+                        const bool has = ent[u] != TOP_INVALID && !(a.dbg & 1);
+                        if (!__any_sync(0xFFFFFFFFu, has)) continue;
+                        const int dot = (int)(ent[u] >> 35), n2b = (int)((ent[u] >> 8) & 0x7FFFFFFull);
+                        const int id = colbase + (int)(ent[u] & 0xFFull);
+                        const bool nz = n2a_i > 0 && n2b > 0;           // a zero descriptor scores 0 whatever the dot product: key (0, 1)
+                        const float s32 = nz ? (float)dot * rsqrtf((float)n2b) * ra : 0.f;
+                        // stale candidates (staged under an older threshold) are dropped on the image of the 8th entry
+                        const bool live = has && (bi[7] < 0 || s32 >= ts[7] * (1.f - 4e-6f));
+                        if (!__any_sync(0xFFFFFFFFu, live)) { n_stale += has; continue; }
+                        mad_top8f_insert(ts, td, tn, bi, live, s32, nz ? dot : 0, nz ? n2b : 1, id);
+                        changed |= live;
+                        n_ins += live;
+                        n_stale += has && !live;
+                    }
+                    if (a.dbg & 32) {
+                        n_ins = __reduce_add_sync(0xFFFFFFFFu, n_ins);
+                        n_stale = __reduce_add_sync(0xFFFFFFFFu, n_stale);
+                        if (lane == 0) {
+                            atomicAdd(&g_top_dbg[4], 1ull); atomicAdd(&g_top_dbg[5], (unsigned long long)(clock64() - dc0));
+                            atomicAdd(&g_top_dbg[6], (unsigned long long)n_ins); atomicAdd(&g_top_dbg[7], (unsigned long long)n_stale);
+                        }
+                    }
+                    // fp32 image of the 8th entry's score (error < 1e-6) minus the pre-filter margin
+                    // (atomicMax on the int image: thresholds are >= 0 or the initial -1, and the epilogue threads seed the
+                    //  same word with the 8th score of their local lists)
+                    if (changed && bi[7] >= 0) atomicMax(reinterpret_cast<int*>(const_cast<float*>(&s_thr8[dq * 32 + lane])), __float_as_int(fmaxf(ts[7] - 4e-6f, 0.f)));
+                }
+            }
+            if (!any) {
+                if (done == 2) break;                                // flags read BEFORE the scan that found nothing
+                // idle: poll a few times per tile only (a polling loop that spins every ~100 cycles in four warps took a
+                // quarter of the SM's issue slots away from the epilogue warps: +25 % on the whole sweep)
+                __nanosleep(a.dbg & 16 ? 32 : (a.dbg & 64 ? 1000 : 300));
+            }
+        }
+        if (row < a.M) {                                             // list 0 of the 3 lists of (segment, row)
+            const long long o = ((long long)(seg * 3) * a.M + row) * a.k;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (i < a.k) {
+                    a.topk_idx[o + i] = timeout ? -2 : bi[i];
+                    a.topk_score[o + i] = bi[i] < 0 ? -INFINITY : (td[i] == 0 ? 0.0 : mad_score(td[i], (double)n2a_i, (double)tn[i]));
+                }
+        }
+    } else if (warp >= 4 && warp < 4 + EPI_WARPS) {
         // ===================== epilogue: thread = one hi row =====================
         const int q = warp & 3;                                      // TMEM lane quadrant of this warp
         const int ew = warp - 4;                                     // epilogue warp 0..7
@@ -417,18 +527,35 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         unsigned long long* my_key = stg_key + ew * STG;
         int* my_dot = stg_dot + ew * STG;
         constexpr bool kTop = (MODE == MODE_TOPK || MODE == MODE_TOP8);
-        constexpr int kList = (MODE == MODE_TOPK) ? MAD_TOPK_MAX : (MODE == MODE_TOP8 ? 8 : 1);
-        double bs[kList];
+        constexpr int kList = (MODE == MODE_TOPK) ? MAD_TOPK_MAX : 1;
+        double bs[kList];                                            // MODE_TOPK (k > 8): the list lives in the epilogue thread
         int bi[kList];
         float thr = -1.f;                                            // fp32 bound of the current worst list entry
-        int td[8], tn[8];                                            // TOP8: integer-keyed list (dot, |lo|^2); scores at the end
-        if (kTop) {
+        if (MODE == MODE_TOPK) {
 #pragma unroll
             for (int i = 0; i < kList; ++i) { bs[i] = -INFINITY; bi[i] = -1; }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) { td[i] = 0; tn[i] = 1; }
         }
-        const int k_last = (MODE == MODE_TOP8) ? 7 : a.k - 1;        // TOP8 keeps 8 entries whatever k <= 8 is
+        const int k_last = a.k - 1;
+        int top_cnt = 0;                                             // TOP8: entries this lane has staged in the current half
+        float ls[8];                                                 // TOP8: thread-local list of the first TOP_LOCAL_TILES tiles
+        int ld[8], ln[8], li[8];
+        if (MODE == MODE_TOP8) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { ls[i] = 0.f; ld[i] = 0; ln[i] = 1; li[i] = -1; }
+        }
+        auto flush_local = [&]() {                                   // the local list becomes list 1 + grp of (segment, row); its
+                                                                     // 8th score seeds the row's threshold for the staged phase
+            if (li[7] >= 0) atomicMax(reinterpret_cast<int*>(const_cast<float*>(&s_thr8[q * 32 + lane])), __float_as_int(fmaxf(ls[7] - 4e-6f, 0.f)));
+            if (row_ok) {
+                const long long o = ((long long)(seg * 3 + 1 + grp) * a.M + row) * a.k;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (i < a.k) {
+                        a.topk_idx[o + i] = li[i];
+                        a.topk_score[o + i] = li[i] < 0 ? -INFINITY : (ld[i] == 0 ? 0.0 : mad_score(ld[i], n2a, (double)ln[i]));
+                    }
+            }
+        };
         // Candidates that pass the fp32 pre-filter are only STAGED here (two shared-memory stores); the drain warps take
         // the float64 decision and write the pairs.
         int stg_n = 0;                                               // candidates staged by this warp (warp-uniform register)
@@ -448,6 +575,19 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                 cur ^= 1;
                 __syncwarp();
             }
+        };
+        auto publish_top = [&](int t) {                              // TOP8: hand the current half (entries of tile t) to the drain warp
+            __syncwarp();
+            if (lane == 0) {
+                mad_st_release_cta(&s_half[2 * ew + cur], t + 1);    // (the lanes' entries are ordered before it by the __syncwarp)
+                long long spins = 0;
+                const long long c0 = (a.dbg & 32) ? clock64() : 0;
+                while (mad_ld_acquire_cta(&s_half[2 * ew + (cur ^ 1)]) != 0 && ++spins < (1LL << 26)) __nanosleep(32);   // other half still in use
+                if (a.dbg & 32) { atomicAdd(&g_top_dbg[1], (unsigned long long)(clock64() - c0)); atomicAdd(&g_top_dbg[2], 1ull); }
+            }
+            cur ^= 1;
+            top_cnt = 0;
+            __syncwarp();
         };
         // Work split between the two epilogue groups.  One-CTA kernel (128-wide tiles, 4 accumulators): the
         // groups alternate tiles.  Pair kernel (256-wide tiles, only 2 accumulators fit TMEM): both groups
@@ -477,10 +617,14 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         int it = kSplitCols ? 0 : grp;                               // position of the tile in this CTA's sweep
         int par = 0;                                                 // which rnorm buffer holds the current tile
         if (t_first < t_end) stage_rb(t_first, 0);
-        for (int t = t_first; t < t_end; t += kStep, it += kStep, par ^= 1) {
+        // The tile loop exists twice: the first TOP_LOCAL_TILES tiles of a top-8 sweep run with the thread-local list
+        // (top_local), all others without it -- as ONE loop the list stayed live for the whole sweep and was spilled and
+        // reloaded around every tile.
+        auto tile_body = [&](auto local_tag, const int t, const int it, const int par) {
             const int acc = it % NACC;
             const uint32_t acc_phase = (uint32_t)(it / NACC) & 1u;
             const int n0 = t * TN;
+            constexpr bool top_local = decltype(local_tag)::value;   // (two instantiations: the local list's registers are dead in the second)
             group_sync();                                            // this tile's norms are staged; the other buffer is free
             if (t + kStep < t_end) stage_rb(t + kStep, par ^ 1);     // this group's next tile: latency hidden by this tile
             const float* rbt = my_rb + par * 256 - c_lo;             // indexed by the column inside the tile
@@ -491,29 +635,85 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             for (int c0 = c_lo; c0 < c_lo + BN; c0 += 32) {
                 uint32_t v[32];
                 tmem_ld32(taddr + (uint32_t)c0, v);
-                float rb[32];
-#pragma unroll
-                for (int j4 = 0; j4 < 8; ++j4) {
-                    const float4 r4 = reinterpret_cast<const float4*>(rbt + c0)[j4];
-                    rb[4 * j4] = r4.x; rb[4 * j4 + 1] = r4.y; rb[4 * j4 + 2] = r4.z; rb[4 * j4 + 3] = r4.w;
-                }
                 tmem_ld_wait();
+                if (c0 == c_lo + BN - 32 && !(a.dbg & 4)) {
+                    // the tile's last 32 columns are in registers: the accumulator goes back to the MMA warp NOW, so the
+                    // processing of this chunk (a quarter of the epilogue) is off the tensor pipe's critical path
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {                                 // 4 (x2 in a pair) arrivals free the accumulator
+                        if (NCTA == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
+                    }
+                }
                 // Branch-free pre-filter over the 32 columns (the epilogue must stay small: an unrolled
                 // branchy body overflowed the instruction cache and made the epilogue the bottleneck);
                 // the rare candidates are then fetched again from TMEM one column at a time.
                 float thr_eff = thr;
-                if (kTop && kSplitCols) thr_eff = fmaxf(thr, s_thr[(grp ^ 1) * BM + q * 32 + lane]);
+                if (MODE == MODE_TOPK && kSplitCols) thr_eff = fmaxf(thr, s_thr[(grp ^ 1) * BM + q * 32 + lane]);
+                if (MODE == MODE_TOP8)                                // local phase: this thread's own 8th score; then the row's threshold
+                    thr_eff = top_local ? (li[7] < 0 ? -1.f : ls[7] - 4e-6f) : s_thr8[q * 32 + lane];   // as published by its drain warp
                 const float lim = kTop ? (row_ok && ra > 0.f ? thr_eff / ra : INFINITY) : thr_pairs;
                 unsigned mask = 0;
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float sc = (float)(int)v[j] * rb[j];
-                    const bool pass = kTop ? (sc >= lim) : (sc > lim);
-                    mask |= (pass ? 1u : 0u) << j;
+                for (int j4 = 0; j4 < 8; ++j4) {                     // 1/|lo| of four columns at a time (not 32 registers held)
+                    const float4 r4 = reinterpret_cast<const float4*>(rbt + c0)[j4];
+                    const float rb[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float sc = (float)(int)v[4 * j4 + u] * rb[u];
+                        const bool pass = kTop ? (sc >= lim) : (sc > lim);
+                        mask |= (pass ? 1u : 0u) << (4 * j4 + u);
+                    }
                 }
                 // zero row: every score is 0 and ties go to the lowest index -- only the first k columns matter
-                if (kTop && row_ok && ra == 0.f) mask = (bi[MODE == MODE_TOP8 ? 7 : k_last] < 0) ? 0xFFFFFFFFu : 0u;
-                if (kTop) {
+                if (MODE == MODE_TOPK && row_ok && ra == 0.f) mask = (bi[k_last] < 0) ? 0xFFFFFFFFu : 0u;
+                if (MODE == MODE_TOP8) {
+                    // zero row: only the first 8 columns of the sweep can make its list (score 0, lowest indices)
+                    if (row_ok && ra == 0.f) mask = (t == t_begin && c0 == 0) ? 0xFFu : 0u;
+                    const int left = a.N - (n0 + c0);                // columns of this chunk that exist
+                    if (left < 32) mask &= (left <= 0) ? 0u : ((1u << left) - 1u);
+                    if (a.dbg & 2) mask = 0u;
+                    if (top_local) {
+                        // thread-local phase: one ballot per round, all lanes with a candidate run the (float32-image) insertion
+                        // network together; a candidate is re-checked against the list as it is NOW
+                        for (;;) {
+                            if (__ballot_sync(0xFFFFFFFFu, mask != 0u) == 0u) break;
+                            const bool has = mask != 0u;
+                            const int j = has ? __ffs(mask) - 1 : 0;
+                            mask &= mask - 1;
+                            const int dot = (int)mad_select32(v, j);
+                            const int n2b = __float_as_int(rbt[c0 + j + 128]);
+                            const bool nz = n2a_i > 0 && n2b > 0;
+                            const float s32 = nz ? (float)dot * rbt[c0 + j] * ra : 0.f;
+                            const bool live = has && (li[7] < 0 || s32 >= ls[7] * (1.f - 4e-6f));
+                            if (__any_sync(0xFFFFFFFFu, live))
+                                mad_top8f_insert(ls, ld, ln, li, live, s32, nz ? dot : 0, nz ? n2b : 1, a.lo_index_base + n0 + c0 + j);
+                        }
+                        continue;
+                    }
+                    // Candidates are only STAGED (one 8-byte shared-memory store each, into this lane's own slots): one ballot
+                    // per round, as in pairs mode; the drain warp that owns the row's list takes it from there.
+                    const long long rc0 = (a.dbg & 32) ? clock64() : 0;
+                    int n_rounds = 0;
+                    for (;;) {
+                        const unsigned b = __ballot_sync(0xFFFFFFFFu, mask != 0u);
+                        if (b == 0u) break;
+                        ++n_rounds;
+                        if (__ballot_sync(0xFFFFFFFFu, mask != 0u && top_cnt == TOP_SLOTS) != 0u) publish_top(t);
+                        if (mask) {
+                            const int j = __ffs(mask) - 1;
+                            mask &= mask - 1;
+                            const unsigned long long dot = (unsigned long long)mad_select32(v, j);
+                            const unsigned long long n2b = (unsigned long long)(unsigned)__float_as_int(rbt[c0 + j + 128]);
+                            top_slots[((ew * 2 + cur) * 32 + lane) * TOP_SLOTS + top_cnt] = (dot << 35) | (n2b << 8) | (unsigned long long)(c0 + j);
+                            ++top_cnt;
+                        }
+                    }
+                    if ((a.dbg & 32) && lane == 0 && n_rounds) {
+                        atomicAdd(&g_top_dbg[0], (unsigned long long)(clock64() - rc0));
+                        atomicAdd(&g_top_dbg[3], (unsigned long long)n_rounds);
+                    }
+                } else if (kTop) {
                     // each lane walks its own (rare) candidates; the value comes out of the registers
                     // through a select tree, so lanes with candidates in different columns run together
                     while (mask) {
@@ -523,14 +723,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                         const int col = n0 + c0 + j;
                         if (col < a.N) {
                             const int n2b = __float_as_int(rbt[c0 + j + 128]);                       // |lo|^2 from the tile buffer
-                            if (MODE == MODE_TOP8) {
-                                // a zero descriptor scores 0 whatever the dot product: key (0, 1)
-                                const bool nz = n2a_i > 0 && n2b > 0;
-                                mad_top8i_insert(td, tn, reinterpret_cast<int(&)[8]>(bi), nz ? dot : 0, nz ? n2b : 1, a.lo_index_base + col);
-                                // fp32 image of the 8th entry's score (error < 1e-6) minus the pre-filter margin
-                                thr = (bi[7] < 0) ? -1.f : (float)td[7] * ra * rsqrtf((float)tn[7]) - 4e-6f;
-                                if (kSplitCols) s_thr[grp * BM + q * 32 + lane] = thr;
-                            } else {
+                            {
                                 const double s = mad_score(dot, n2a, (double)n2b);
                                 mad_topk_insert(bs, bi, a.k, s, a.lo_index_base + col);
                                 thr = (bi[k_last] < 0) ? -1.f : (float)bs[k_last] - 4e-6f;
@@ -565,30 +758,34 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {                                         // 4 (x2 in a pair) arrivals free the accumulator
-                if (NCTA == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc));
+            if (a.dbg & 4) {                                         // (measurement: release at the end of the tile's epilogue)
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) { if (NCTA == 2) mbar_arrive_leader(tempty_bar(acc)); else mbar_arrive(tempty_bar(acc)); }
             }
+            // TOP8: the tile's candidates go to the drain warp now (a half never mixes tiles: its state word names the tile),
+            // so a row's threshold lags by at most one tile
+            if (MODE == MODE_TOP8 && __ballot_sync(0xFFFFFFFFu, top_cnt > 0) != 0u) publish_top(t);
+        };
+        int t = t_first;
+        if (MODE == MODE_TOP8) {
+            for (int n = 0; n < TOP_LOCAL_TILES && t < t_end; ++n, t += kStep, it += kStep, par ^= 1) tile_body(std::true_type{}, t, it, par);
+            flush_local();
         }
+        for (; t < t_end; t += kStep, it += kStep, par ^= 1) tile_body(std::false_type{}, t, it, par);
         if (!kTop) {
             publish(stg_n);
             __syncwarp();
             if (lane == 0) { __threadfence_block(); s_done[ew] = 1; }
         }
-        if (kTop && row_ok) {
+        if (MODE == MODE_TOP8) {
+            __syncwarp();
+            if (lane == 0) mad_st_release_cta(&s_done[ew], 1);
+        }
+        if (MODE == MODE_TOPK && row_ok) {
             // one partial list per (segment, epilogue group): the host merges 2 S lists
             const long long o = ((long long)(seg * 2 + grp) * a.M + row) * a.k;
-            if (MODE == MODE_TOP8) {
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    if (i < a.k) {
-                        a.topk_idx[o + i] = bi[i];
-                        a.topk_score[o + i] = bi[i] < 0 ? -INFINITY : (td[i] == 0 ? 0.0 : mad_score(td[i], n2a, (double)tn[i]));
-                    }
-            } else {
-                for (int i = 0; i < a.k; ++i) { a.topk_idx[o + i] = bi[i]; a.topk_score[o + i] = bs[i]; }
-            }
+            for (int i = 0; i < a.k; ++i) { a.topk_idx[o + i] = bi[i]; a.topk_score[o + i] = bs[i]; }
         }
     }
     tc_fence_before();
@@ -753,6 +950,7 @@ int mad_match_u8_pairs(const void* hi_u8, int M, int M_pad, const void* lo_u8, i
     a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN * ncta), a.S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = cc;
     a.cand_key = cand_key; a.cand_dot = cand_dot; a.cap = cap; a.count = count;
+    a.dbg = getenv("MAD_TOPK_DBG") ? atoi(getenv("MAD_TOPK_DBG")) : 0;
     MAD_PROF("match_u8_pairs_kernel", st);
     return launch_u8<MODE_PAIRS>(ncta, M, a.S, map_hi, map_lo, a, st);
 }
@@ -769,6 +967,23 @@ int mad_match_u8_topk(const void* hi_u8, int M, int M_pad, const void* lo_u8, in
     a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN * ncta), S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = 0.0;
     a.k = k; a.lo_index_base = lo_index_base; a.topk_idx = topk_idx; a.topk_score = topk_score;
-    MAD_PROF("match_u8_topk_kernel", st);
-    return k <= 8 ? launch_u8<MODE_TOP8>(ncta, M, S, map_hi, map_lo, a, st) : launch_u8<MODE_TOPK>(ncta, M, S, map_hi, map_lo, a, st);
+    a.dbg = getenv("MAD_TOPK_DBG") ? atoi(getenv("MAD_TOPK_DBG")) : 0;
+    if (a.dbg & 32) {
+        unsigned long long z[8] = {0};
+        cudaMemcpyToSymbolAsync(g_top_dbg, z, sizeof(z), 0, cudaMemcpyHostToDevice, st);
+    }
+    {
+        MAD_PROF("match_u8_topk_kernel", st);
+        rc = k <= 8 ? launch_u8<MODE_TOP8>(ncta, M, S, map_hi, map_lo, a, st) : launch_u8<MODE_TOPK>(ncta, M, S, map_hi, map_lo, a, st);
+    }
+    if (rc == MAD_OK && (a.dbg & 32)) {
+        unsigned long long z[8];
+        cudaStreamSynchronize(st);
+        cudaMemcpyFromSymbol(z, g_top_dbg, sizeof(z));
+        const double ctas = (double)(ncta == 2 ? 2 * mad_ceil_div(M, 2 * BM) : mad_ceil_div(M, BM)) * S;
+        fprintf(stderr, "[top8 dbg] per CTA: round cycles %.0f (per epilogue warp %.0f), publish-wait cycles %.0f, publishes %.0f, rounds %.0f, "
+                        "drain passes %.0f, drain busy cycles %.0f (per drain warp %.0f), inserted %.0f, stale %.0f\n",
+                z[0] / ctas, z[0] / ctas / 8, z[1] / ctas, z[2] / ctas, z[3] / ctas, z[4] / ctas, z[5] / ctas, z[5] / ctas / 4, z[6] / ctas, z[7] / ctas);
+    }
+    return rc;
 }
