@@ -109,7 +109,7 @@ def cpu_crops(grid, n_crops, side):
     return [np.ascontiguousarray(grid[x:x + side, y:y + side, z:z + side]) for _, x, y, z in cands[:n_crops]]
 
 
-def cpu_stage_sample(grid, voxelsp, procs, steps, warmup, v1_full):
+def cpu_stage_sample(grid, voxelsp, procs, steps, warmup, v1_full, K=C2_K, D=C2_D, M=C2_M, n_vox=None):
     """The reference's CPU path on the C2 map, sampled STAGE BY STAGE in each stage's own unit and scaled to the whole map:
     build_space + find_anchors per padded base voxel (an 80^3 occupancy-matched crop), assign_orientations per keypoint
     (48 keypoints of the crop), generate_descriptors per oriented feature (160 of them), the two matching lines per scored
@@ -133,14 +133,14 @@ def cpu_stage_sample(grid, voxelsp, procs, steps, warmup, v1_full):
             res = pool.map(_cpu_stage_worker, jobs)
         dt = (time.perf_counter() - t0) / max(steps, 1)
     unit = {k: float(np.mean([r[k] for r in res])) for k in res[0] if k != "seconds"}
-    t_map = (unit["build_per_voxel"] * v1_full + unit["detect_per_voxel"] * v1_full + unit["orient_per_kp"] * C2_K +
-             unit["describe_per_feature"] * C2_D + unit["match_per_pair"] * C2_M * C2_D)
+    t_map = (unit["build_per_voxel"] * v1_full + unit["detect_per_voxel"] * v1_full + unit["orient_per_kp"] * K +
+             unit["describe_per_feature"] * D + unit["match_per_pair"] * M * D)
     unit["seconds_per_map_one_process"] = t_map
     unit["stage_seconds_per_map"] = {"build_space": unit["build_per_voxel"] * v1_full, "find_anchors": unit["detect_per_voxel"] * v1_full,
-                                     "assign_orientations": unit["orient_per_kp"] * C2_K,
-                                     "generate_descriptors": unit["describe_per_feature"] * C2_D,
-                                     "match": unit["match_per_pair"] * C2_M * C2_D}
-    return procs * C2["n"] ** 3 / t_map, dt, unit
+                                     "assign_orientations": unit["orient_per_kp"] * K,
+                                     "generate_descriptors": unit["describe_per_feature"] * D,
+                                     "match": unit["match_per_pair"] * M * D}
+    return procs * (n_vox if n_vox else C2["n"] ** 3) / t_map, dt, unit
 
 
 CPU_SAMPLE_TEXT = ("stage-wise sample of the C2 map per process: build_space + find_anchors on an %d^3 occupancy-matched crop "
@@ -578,13 +578,6 @@ def bench_c5(ctx, args):
 # ---------------------------------------------------------------------------------------------
 # C4: a batch of 64 snapshot maps, map i -> rank i mod N
 # ---------------------------------------------------------------------------------------------
-def _c4_cpu_one(job):
-    import mad_oracle as mo
-    t0 = time.perf_counter()
-    mo.describe_struct(job, 1.0)
-    return time.perf_counter() - t0
-
-
 def bench_c4(ctx, args):
     torch = ctx.torch
     from mad_b200 import pipeline as P
@@ -663,16 +656,14 @@ def bench_c4(ctx, args):
         "verified_equal_to_1gpu": verified,
     }
     if not args.no_cpu_baseline and world == 1:
-        import multiprocessing as mp
-        procs = min(host_procs(), 8)
-        jobs = [grids[i % len(grids)] for i in range(procs)]
-        with mp.get_context("fork").Pool(procs) as pool:
-            t0 = time.perf_counter()
-            pool.map(_c4_cpu_one, jobs)
-            dt = time.perf_counter() - t0
-        res_line["cpu_baseline"] = {"value": procs * 96 ** 3 / dt, "unit": "voxels/s", "cores": procs, "kind": "port",
-                                    "sample": "%d of the 64 snapshot maps, one per process (oracle/mad_oracle.py describe_struct)" % procs,
-                                    "seconds": dt}
+        procs = host_procs()
+        k_map, d_map = K_tot / n_maps, D_tot / n_maps
+        v, s_per, unit = cpu_stage_sample(grids[0], 1.0, procs, 1, 0, V1, K=k_map, D=d_map, M=0, n_vox=96 ** 3)
+        res_line["cpu_baseline"] = {"value": v, "unit": "voxels/s", "cores": procs, "kind": "port", "seconds": s_per,
+                                    "sample": "stage-wise sample of one snapshot map per process (as for C2: %d^3 crop, %d keypoints, %d oriented "
+                                              "features) scaled to a map's V1 = 114^3, K = %.0f, D = %.0f; one map per process on all host cores"
+                                              % (CPU_CROP, CPU_KP, CPU_OF, k_map, d_map),
+                                    "per_unit_seconds": unit}
     return res_line
 
 

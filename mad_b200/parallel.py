@@ -48,20 +48,26 @@ def gather_topk(idx_local, score_local, group=None):
 
 def gather_varlen(t, group=None):
     """all_gather of tensors whose first dimension differs per rank (pair lists, descriptor tables):
-    counts first, then one padded all_gather; returns the list of per-rank tensors."""
+    counts first, then one padded all_gather; returns the list of per-rank tensors.  Rows travel as raw bytes, so any
+    dtype works (NCCL has no int16)."""
     g = _world(group)
     if g == 1:
         return [t]
+    row_shape = tuple(t.shape[1:])
+    row_bytes = t.element_size()
+    for d in row_shape:
+        row_bytes *= int(d)
     n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
     counts = [torch.zeros_like(n) for _ in range(g)]
     dist.all_gather(counts, n, group=group)
     counts = [int(c.item()) for c in counts]
     cap = max(max(counts), 1)
-    pad = torch.zeros((cap,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
-    pad[: t.shape[0]] = t
+    pad = torch.zeros((cap, row_bytes), dtype=torch.uint8, device=t.device)
+    if t.shape[0]:
+        pad[: t.shape[0]] = t.contiguous().view(-1).view(torch.uint8).view(t.shape[0], row_bytes)
     bufs = [torch.empty_like(pad) for _ in range(g)]
     dist.all_gather(bufs, pad, group=group)
-    return [b[:c] for b, c in zip(bufs, counts)]
+    return [b[:c].contiguous().view(-1).view(t.dtype).view((c,) + row_shape) for b, c in zip(bufs, counts)]
 
 
 def match_topk_sharded(hi_set, lo_shard_set, k, lo_index_base, group=None, impl=None):
