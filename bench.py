@@ -348,7 +348,9 @@ def bench_c2(ctx, args):
         pairs = P.match_threshold(hi_all, lo, 0.6, impl=args.match_impl)
         return sp, kp, ori, dsc, pairs
 
-    stream_api = P.MapStream(hi=hi_all, cc=0.6, exact_f64=exact, match_impl=args.match_impl)
+    # e2e uses the compact wire format (uint8 descriptors, (hi, lo, exact dot) pairs + norms; the host widens / recomputes
+    # the float64 scores bit for bit: tests/test_gpu_parity.py::test_map_stream_compact_format)
+    stream_api = P.MapStream(hi=hi_all, cc=0.6, exact_f64=exact, match_impl=args.match_impl, compact=not args.full_format)
 
     def run_e2e(n_steps):
         prev, out = None, None
@@ -465,6 +467,8 @@ def bench_c2(ctx, args):
                    "exact_f64": exact, "gradient_tiles_computed": {"up": round(grad_frac[0], 4), "base": round(grad_frac[1], 4)}},
         "e2e": {"value": ctx.world * n_vox / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(grid_pin.numel() * 4), "d2h_bytes_per_step": d2h, "d2h_detail": d2h_detail,
+                "d2h_format": "full (int16 descriptors, float64 scores)" if args.full_format else
+                              "compact (uint8 descriptors, int32 dot per pair + int32 squared norms; widened / scored on the host bit for bit)",
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -677,6 +681,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--match-impl", type=int, default=None, help="default: product (uint8 tcgen05 one-pass); 1 = SIMT check, 2 = fp16 tcgen05")
     ap.add_argument("--exact", type=int, default=1, help="1 = float64 line accumulation (bit-exact with SciPy)")
+    ap.add_argument("--full-format", action="store_true", help="e2e downloads int16 descriptors and float64 scores instead of the compact format")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     if args.impl == "reference":

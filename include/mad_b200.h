@@ -256,6 +256,12 @@ size_t mad_match_pairs_finish_workspace_bytes(long long n);
 int mad_match_pairs_finish(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows, int lo_rows,
                            const int32_t* hi_n2, const int32_t* lo_n2, int32_t* pair_hi, int32_t* pair_lo,
                            double* pair_score, void* workspace, size_t workspace_bytes, void* stream);
+/* Compact form for the trip to the host: pair_dot = the exact integer dot product instead of the float64 score (12 bytes
+ * per pair instead of 16); score = dot / sqrt(|hi|^2 |lo|^2) is recomputed from the norms with the same correctly rounded
+ * float64 operations (mad_b200.pipeline.scores_from_dots), i.e. bit-identical to mad_match_pairs_finish's. */
+int mad_match_pairs_finish_dot(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows, int lo_rows,
+                               int32_t* pair_hi, int32_t* pair_lo, int32_t* pair_dot, void* workspace, size_t workspace_bytes,
+                               void* stream);
 
 /* Top-k mode (extension): per hi row the k best lo rows by (score desc, index asc);
  * lo_index_base is added to the stored indices (sharded reference axis).  k <= 32.

@@ -85,6 +85,7 @@ SIGNATURES = {
     "mad_match_pairs": (_I, [C.POINTER(MadDscSet), C.POINTER(MadDscSet), C.c_double, _P, _P, C.c_uint64, _P, _P]),
     "mad_match_pairs_finish_workspace_bytes": (_SZ, [C.c_longlong]),
     "mad_match_pairs_finish": (_I, [_P, _P, C.c_longlong, _I, _I, _P, _P, _P, _P, _P, _P, _SZ, _P]),
+    "mad_match_pairs_finish_dot": (_I, [_P, _P, C.c_longlong, _I, _I, _P, _P, _P, _P, _SZ, _P]),
     "mad_dsc_norms": (_I, [_P, _I, _P, _P]),
     "mad_dsc_to_half": (_I, [_P, _I, _I, _P, _P]),
     "mad_match_segments": (_I, [_I, _I, _I]),

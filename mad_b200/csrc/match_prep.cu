@@ -74,6 +74,19 @@ __global__ void pairs_finish_kernel(const unsigned long long* __restrict__ key, 
     score[i] = mad_score(dot[i], (double)__ldg(hi_n2 + row), (double)__ldg(lo_n2 + col));
 }
 
+// Compact form: the exact integer dot product instead of the float64 score (12 instead of 16 bytes per pair on the way to
+// the host, which recomputes dot / sqrt(|hi|^2 |lo|^2) from the norms with the same correctly rounded operations).
+__global__ void pairs_finish_dot_kernel(const unsigned long long* __restrict__ key, const int32_t* __restrict__ dot, long long n,
+                                        unsigned long long lo_rows, int32_t* __restrict__ pair_hi, int32_t* __restrict__ pair_lo,
+                                        int32_t* __restrict__ pair_dot) {
+    const long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long k = key[i];
+    pair_hi[i] = (int)(k / lo_rows);
+    pair_lo[i] = (int)(k % lo_rows);
+    pair_dot[i] = dot[i];
+}
+
 // The candidate counter is reset by a kernel, not cudaMemsetAsync: a memset may be routed through a
 // copy engine and then queues behind a large device-to-host copy of another stream (observed: the
 // matching kernel waited 1.4 ms for the descriptor table's copy-out).
@@ -138,12 +151,34 @@ extern "C" int mad_match_pairs(const MadDscSet* hi, const MadDscSet* lo, double 
 
 extern "C" size_t mad_match_pairs_finish_workspace_bytes(long long n) { return finish_layout(n).total; }
 
+static int pairs_finish_impl(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows, int lo_rows,
+                             const int32_t* hi_n2, const int32_t* lo_n2, int32_t* pair_hi, int32_t* pair_lo, double* pair_score,
+                             int32_t* pair_dot, void* workspace, size_t workspace_bytes, void* stream);
+
 extern "C" int mad_match_pairs_finish(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows,
                                       int lo_rows, const int32_t* hi_n2, const int32_t* lo_n2, int32_t* pair_hi, int32_t* pair_lo,
                                       double* pair_score, void* workspace, size_t workspace_bytes, void* stream) {
     MAD_CHECK_ARG(n >= 0 && n < (1LL << 31));
     if (n == 0) return MAD_OK;
-    MAD_CHECK_ARG(cand_key && cand_dot && hi_n2 && lo_n2 && pair_hi && pair_lo && pair_score && workspace && hi_rows > 0 && lo_rows > 0);
+    MAD_CHECK_ARG(hi_n2 && lo_n2 && pair_score);
+    return pairs_finish_impl(cand_key, cand_dot, n, hi_rows, lo_rows, hi_n2, lo_n2, pair_hi, pair_lo, pair_score, nullptr, workspace,
+                             workspace_bytes, stream);
+}
+
+extern "C" int mad_match_pairs_finish_dot(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows, int lo_rows,
+                                          int32_t* pair_hi, int32_t* pair_lo, int32_t* pair_dot, void* workspace,
+                                          size_t workspace_bytes, void* stream) {
+    MAD_CHECK_ARG(n >= 0 && n < (1LL << 31));
+    if (n == 0) return MAD_OK;
+    MAD_CHECK_ARG(pair_dot);
+    return pairs_finish_impl(cand_key, cand_dot, n, hi_rows, lo_rows, nullptr, nullptr, pair_hi, pair_lo, nullptr, pair_dot, workspace,
+                             workspace_bytes, stream);
+}
+
+static int pairs_finish_impl(const uint64_t* cand_key, const int32_t* cand_dot, long long n, int hi_rows, int lo_rows,
+                             const int32_t* hi_n2, const int32_t* lo_n2, int32_t* pair_hi, int32_t* pair_lo, double* pair_score,
+                             int32_t* pair_dot, void* workspace, size_t workspace_bytes, void* stream) {
+    MAD_CHECK_ARG(cand_key && cand_dot && pair_hi && pair_lo && workspace && hi_rows > 0 && lo_rows > 0);
     const FinishLayout L = finish_layout(n);
     MAD_CHECK_ARG(workspace_bytes >= L.total);
     cudaStream_t st = (cudaStream_t)stream;
@@ -159,8 +194,12 @@ extern "C" int mad_match_pairs_finish(const uint64_t* cand_key, const int32_t* c
                                                  key_sorted, cand_dot, dot_sorted, (int)n, 0, key_bits, st));
     }
     MAD_PROF("pairs_finish_kernel", st);
-    pairs_finish_kernel<<<(unsigned)mad_ceil_div(n, 256), 256, 0, st>>>(key_sorted, dot_sorted, n, (unsigned long long)lo_rows, hi_n2, lo_n2, pair_hi,
-                                                                       pair_lo, pair_score);
+    if (pair_dot)
+        pairs_finish_dot_kernel<<<(unsigned)mad_ceil_div(n, 256), 256, 0, st>>>(key_sorted, dot_sorted, n, (unsigned long long)lo_rows, pair_hi,
+                                                                               pair_lo, pair_dot);
+    else
+        pairs_finish_kernel<<<(unsigned)mad_ceil_div(n, 256), 256, 0, st>>>(key_sorted, dot_sorted, n, (unsigned long long)lo_rows, hi_n2, lo_n2,
+                                                                           pair_hi, pair_lo, pair_score);
     MAD_LAUNCH_OK();
     return MAD_OK;
 }

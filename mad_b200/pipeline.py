@@ -471,9 +471,20 @@ def _pick_impl_explicit(hi, lo, impl):
 _PAIR_CAP = {}
 
 
-def match_threshold(hi, lo, cc=0.6, impl=None):
+def scores_from_dots(pair_hi, pair_lo, pair_dot, hi_norm2, lo_norm2):
+    """Host side of the compact pair format: float64 cosine scores from the exact integer dot products and squared norms,
+    with the operations of the device's mad_score (multiply, sqrt, divide: all correctly rounded), hence bit-identical."""
+    p = np.asarray(hi_norm2, dtype=np.float64)[np.asarray(pair_hi)] * np.asarray(lo_norm2, dtype=np.float64)[np.asarray(pair_lo)]
+    out = np.zeros(len(p), dtype=np.float64)
+    nz = p > 0.0
+    out[nz] = np.asarray(pair_dot, dtype=np.float64)[nz] / np.sqrt(p[nz])
+    return out
+
+
+def match_threshold(hi, lo, cc=0.6, impl=None, want="score"):
     """Pairs (i, j) with cosine(hi_i, lo_j) > cc in row-major order (mad/MaD.py:420-424).
-    Returns (hi index int32 [P], lo index int32 [P], score float64 [P]) as device tensors.
+    Returns (hi index int32 [P], lo index int32 [P], score float64 [P]) as device tensors; want="dot" (uint8 kernel only)
+    returns the exact int32 dot products instead of the scores (``scores_from_dots``).
     impl: None/0 = one-pass uint8 tcgen05 kernel + sort (product), 1 = SIMT check kernel,
     2 = fp16 tcgen05 kernel (both two-pass count/fill)."""
     hi, lo = _as_set(hi), _as_set(lo)
@@ -485,7 +496,9 @@ def match_threshold(hi, lo, cc=0.6, impl=None):
         return e, e.clone(), torch.empty(0, dtype=torch.float64, device=dev)
     impl, verify = _pick_impl(hi, lo, impl)
     if impl == 0:
-        return _match_threshold_onepass(hi, lo, cc, dev, st, verify)
+        return _match_threshold_onepass(hi, lo, cc, dev, st, verify, want)
+    if want != "score":
+        raise _lib.MadError("match_threshold: want='dot' is a format of the uint8 kernel (impl 0)")
     n_seg = int(_lib.lib.mad_match_segments(m, lo.rows, impl))
     seg_count = torch.empty(m * n_seg, dtype=torch.int32, device=dev)
     call("mad_match_count", C.byref(hi.c), C.byref(lo.c), C.c_double(cc), n_seg, _ptr(seg_count), impl, st)
@@ -511,7 +524,7 @@ def _read_counts(count, hi, lo):
     return int(vals[0])
 
 
-def _match_threshold_onepass(hi, lo, cc, dev, st, verify=False):
+def _match_threshold_onepass(hi, lo, cc, dev, st, verify=False, want="score"):
     key = (hi.rows, lo.rows)
     cap = _PAIR_CAP.get(key, max(1 << 20, 16 * (hi.rows + lo.rows)))
     while True:
@@ -524,6 +537,8 @@ def _match_threshold_onepass(hi, lo, cc, dev, st, verify=False):
         if p >= (1 << 62):
             raise _lib.MadError("mad_match_pairs: the kernel's internal hand-off timed out (pair list incomplete)")
         if verify and max(hi._max_entry, lo._max_entry) > 255:
+            if want != "score":
+                raise _lib.MadError("match_threshold: entries above 255 need the fp16 kernel, which has no want='dot' form")
             return match_threshold(hi, lo, cc, impl=2)      # entries above 255: the fp16 tensor-core kernel
         if p <= cap:
             break
@@ -531,12 +546,16 @@ def _match_threshold_onepass(hi, lo, cc, dev, st, verify=False):
     _PAIR_CAP[key] = max(cap, p + p // 4)
     pair_hi = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
     pair_lo = torch.empty(max(p, 1), dtype=torch.int32, device=dev)
-    score = torch.empty(max(p, 1), dtype=torch.float64, device=dev)
+    score = torch.empty(max(p, 1), dtype=torch.float64 if want == "score" else torch.int32, device=dev)
     if p:
         ws_bytes = _lib.lib.mad_match_pairs_finish_workspace_bytes(p)
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        call("mad_match_pairs_finish", _ptr(cand_key), _ptr(cand_dot), p, hi.rows, lo.rows, _ptr(hi.norm2), _ptr(lo.norm2),
-             _ptr(pair_hi), _ptr(pair_lo), _ptr(score), _ptr(ws), ws_bytes, st)
+        if want == "score":
+            call("mad_match_pairs_finish", _ptr(cand_key), _ptr(cand_dot), p, hi.rows, lo.rows, _ptr(hi.norm2), _ptr(lo.norm2),
+                 _ptr(pair_hi), _ptr(pair_lo), _ptr(score), _ptr(ws), ws_bytes, st)
+        else:
+            call("mad_match_pairs_finish_dot", _ptr(cand_key), _ptr(cand_dot), p, hi.rows, lo.rows, _ptr(pair_hi), _ptr(pair_lo),
+                 _ptr(score), _ptr(ws), ws_bytes, st)
     return pair_hi[:p], pair_lo[:p], score[:p]
 
 
@@ -619,8 +638,13 @@ class MapStream(object):
 
     ``result`` returns host arrays: dsc int16 [D][1024], kp / ori tables and, with ``hi``, the pair lists."""
 
-    def __init__(self, hi=None, cc=0.6, exact_f64=True, match_impl=None, patch_size=16, depth=2, download=True):
+    def __init__(self, hi=None, cc=0.6, exact_f64=True, match_impl=None, patch_size=16, depth=2, download=True, compact=False):
+        """compact=True: results travel in the compact wire format -- descriptors as the uint8 matching operand
+        (``dsc_u8``; entries are vote counts <= 255, widen with ``.astype(np.int16)``), pairs as (hi, lo, exact int32 dot)
+        + the map's squared norms (``pair_dot``, ``lo_norm2``; ``scores_from_dots`` gives the float64 scores bit for bit):
+        85 MB instead of 140 MB per C2 map over PCIe."""
         _require_cuda()
+        self.compact = bool(compact)
         self.download = download                        # False: results stay on the device (result() returns CUDA tensors)
         self.hi = _as_set(hi) if hi is not None else None
         self.cc, self.exact, self.impl, self.patch = cc, exact_f64, match_impl, patch_size
@@ -666,10 +690,19 @@ class MapStream(object):
             self.gfree[k] = torch.cuda.Event()
             self.gfree[k].record(cur)                       # the upload buffer may be overwritten from here on
         get = (lambda name, t: stage.fetch(name, t, overlap=True)) if self.download else (lambda name, t: t)
-        out = {"dsc": get("dsc", dsc), "kp": get("kp", kp.table[:len(kp)]), "ori": get("ori", ori.table[:len(ori)])}
+        out = {"kp": get("kp", kp.table[:len(kp)]), "ori": get("ori", ori.table[:len(ori)])}
+        lo = DescriptorSet(dsc) if (self.hi is not None or self.compact) else None
+        if self.compact:
+            out.update(dsc_u8=get("dsc8", lo.u8[:lo.rows]), lo_norm2=get("n2", lo.norm2[:lo.rows]))
+        else:
+            out["dsc"] = get("dsc", dsc)
         if self.hi is not None:
-            ph, pl, sc = match_threshold(self.hi, DescriptorSet(dsc), self.cc, impl=self.impl)
-            out.update(pair_hi=get("ph", ph), pair_lo=get("pl", pl), score=get("sc", sc))
+            if self.compact:
+                ph, pl, dot = match_threshold(self.hi, lo, self.cc, impl=self.impl, want="dot")
+                out.update(pair_hi=get("ph", ph), pair_lo=get("pl", pl), pair_dot=get("pd", dot))
+            else:
+                ph, pl, sc = match_threshold(self.hi, lo, self.cc, impl=self.impl)
+                out.update(pair_hi=get("ph", ph), pair_lo=get("pl", pl), score=get("sc", sc))
         stage.mark()
         return stage, out
 

