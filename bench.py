@@ -508,16 +508,30 @@ def bench_c5(ctx, args):
     hi = P.DescriptorSet(hi_pin.to(dev))
     lo = P.DescriptorSet(lo_pin.to(dev))
     stage = P.HostStage()
-    hi_up = torch.empty(tuple(hi_pin.shape), dtype=torch.int16, device=dev)
+    # e2e: every rank needs ALL hi rows, but only 1 / world of them cross its PCIe link: the rank uploads its share and the
+    # shares are all-gathered over NVLink (as int32 words: NCCL has no int16)
+    hs, he = par.shard_bounds(M, world)[rank]
+    hi_share_pin = torch.from_numpy(np.ascontiguousarray(hi_h[hs:he])).pin_memory()
+    share_rows = max(b - a_ for a_, b in par.shard_bounds(M, world))
+    hi_share_up = torch.zeros((share_rows, 1024), dtype=torch.int16, device=dev)
+    hi_all_up = torch.empty((world * share_rows, 1024), dtype=torch.int16, device=dev)
     lo_up = torch.empty(tuple(lo_pin.shape), dtype=torch.int16, device=dev)
 
     def step_device():
         return par.match_topk_sharded(hi, lo, k, s)
 
     def step_e2e():
-        hi_up.copy_(hi_pin, non_blocking=True)
+        hi_share_up[: he - hs].copy_(hi_share_pin, non_blocking=True)
         lo_up.copy_(lo_pin, non_blocking=True)
-        idx, sc = par.match_topk_sharded(P.DescriptorSet(hi_up), P.DescriptorSet(lo_up), k, s)
+        if world > 1:
+            ctx.dist.all_gather_into_tensor(hi_all_up.view(torch.int32), hi_share_up.view(torch.int32))
+            if M % world:                                   # ragged shares: drop each share's padding rows
+                hi_rows = torch.cat([hi_all_up[r * share_rows: r * share_rows + (b - a_)] for r, (a_, b) in enumerate(par.shard_bounds(M, world))])
+            else:
+                hi_rows = hi_all_up
+        else:
+            hi_rows = hi_share_up
+        idx, sc = par.match_topk_sharded(P.DescriptorSet(hi_rows), P.DescriptorSet(lo_up), k, s)
         out = [stage.fetch("idx", idx), stage.fetch("sc", sc)]
         stage.sync()
         return out
@@ -558,7 +572,8 @@ def bench_c5(ctx, args):
                                "[M, k] lists + k-way merge" % (M, N, k, world),
                    "l2": "operands %.0f MB per rank > 126 MB L2" % ((M + e - s) * 1024 / 1e6)},
         "e2e": {"value": M * N / (ms_e2e / steps * 1e-3), "unit": "pairs/s",
-                "h2d_bytes_per_step": int(hi_pin.numel() * 2 + lo_pin.numel() * 2), "d2h_bytes_per_step": d2h,
+                "h2d_bytes_per_step": int(hi_share_pin.numel() * 2 + lo_pin.numel() * 2), "d2h_bytes_per_step": d2h,
+                "note": "per rank: 1 / n_gpus of the hi rows + its lo shard over PCIe; hi shares all-gathered over NVLink",
                 "ms_per_step": ms_e2e / steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "match_u8_topk_kernel", "achieved": ops / (avg * 1e-3) / 1e12,
@@ -594,13 +609,13 @@ def bench_c4(ctx, args):
     pins = [torch.from_numpy(g).pin_memory() for g in grids]
     devs = [p.to(dev) for p in pins]
     n_vox_total = n_maps * 96 ** 3
-    batch = P.MapBatch(streams=int(os.environ.get("MAD_C4_STREAMS", "4")))
+    batch = P.MapBatch(streams=int(os.environ.get("MAD_C4_STREAMS", "4")), compact=not args.full_format)
     like = torch.empty((0, 1024), dtype=torch.int16, device=dev)
 
     def step(host):
         res = batch.run(pins if host else devs, download=host)
         # result collection: per-map descriptor counts of every rank (all-gather); with host=True the tables themselves
-        # have gone to pinned host memory on each rank (rank-local write)
+        # have gone to pinned host memory on each rank (rank-local write; uint8 descriptors unless --full-format)
         counts = torch.tensor([int(r["n_dsc"]) for r in res], dtype=torch.int64, device=dev).reshape(-1, 1)
         return res, par.gather_varlen(counts)
 

@@ -722,9 +722,12 @@ class MapBatch(object):
         results = batch.run(list_of_pinned_grids)          # [{"n_kp", "n_dsc", "dsc", "kp", "ori"}] in input order
     """
 
-    def __init__(self, streams=4, patch_size=16, exact_f64=True):
+    def __init__(self, streams=4, patch_size=16, exact_f64=True, compact=False):
+        """compact=True: descriptors come home as uint8 (``dsc_u8``: vote counts <= 255 for every patch size the reference
+        uses; checked per map, the int16 table is sent instead if an entry is larger) -- half the bytes over PCIe."""
         _require_cuda()
         from concurrent.futures import ThreadPoolExecutor
+        self.compact = bool(compact)
         self.nw = max(1, int(streams))
         self.patch, self.exact = patch_size, exact_f64
         self.device = torch.cuda.current_device()
@@ -752,12 +755,24 @@ class MapBatch(object):
                 r = {"n_kp": len(kp), "n_dsc": len(ori)}
                 if download:
                     st = self.stages[w]
-                    r.update(dsc=st.fetch("dsc%d" % j, dsc), kp=st.fetch("kp%d" % j, kp.table[:len(kp)]),
-                             ori=st.fetch("ori%d" % j, ori.table[:len(ori)]))
+                    r.update(kp=st.fetch("kp%d" % j, kp.table[:len(kp)]), ori=st.fetch("ori%d" % j, ori.table[:len(ori)]))
+                    if self.compact:
+                        ds = DescriptorSet(dsc)
+                        r["_max"] = ds._max_dev
+                        r["dsc_u8"] = st.fetch("dsc8_%d" % j, ds.u8[:ds.rows])
+                        r["_dsc_dev"] = dsc
+                    else:
+                        r["dsc"] = st.fetch("dsc%d" % j, dsc)
                 else:
                     r.update(dsc=dsc, kp=kp.table[:len(kp)], ori=ori.table[:len(ori)])
                 out.append((j, r))
             self.streams[w].synchronize()
+            for _, r in out:                                    # compact: an entry above 255 does not fit the uint8 table
+                if "_max" in r:
+                    if int(r.pop("_max").item()) > 255:
+                        del r["dsc_u8"]
+                        r["dsc"] = r["_dsc_dev"].cpu()
+                    del r["_dsc_dev"]
         return out
 
     def run(self, grids, download=True):
@@ -771,7 +786,7 @@ class MapBatch(object):
             main.wait_stream(s_)
         res = [r for _, r in sorted((x for p in parts for x in p), key=lambda x: x[0])]
         if download:
-            self.last_d2h_bytes = int(sum(r[k].numel() * r[k].element_size() for r in res for k in ("dsc", "kp", "ori")))
+            self.last_d2h_bytes = int(sum(r[k].numel() * r[k].element_size() for r in res for k in ("dsc", "dsc_u8", "kp", "ori") if k in r))
         return res
 
 
