@@ -107,12 +107,10 @@ class MapSpace(object):
             yi -= self.map_padding * self.voxelsp
             zi -= self.map_padding * self.voxelsp
         self.xi, self.yi, self.zi = xi, yi, zi
-        if self.oct_mode != "both":
-            raise NotImplementedError("the CUDA path builds both octaves (oct_mode='both', the only mode "
-                                      "MaD.run uses, mad/MaD.py:359)")
-        self.voxelsp_list = [self.voxelsp / 2, self.voxelsp]
+        self.voxelsp_list = {"both": [self.voxelsp / 2, self.voxelsp], "up": [self.voxelsp / 2],
+                             "base": [self.voxelsp]}[self.oct_mode]                     # mad/MapSpace.py:149-163
         self.space = _P.build_space(grid, self.map_padding, self.sig_init, self.sig_presmooth,
-                                    exact_f64=self.exact_f64, keep_gauss=True, full_gradient=False)
+                                    exact_f64=self.exact_f64, keep_gauss=True, full_gradient=False, oct_mode=self.oct_mode)
         self._cache = {}
 
     # ---- NumPy views of the device arrays (lazy) ------------------------------------------------
@@ -140,7 +138,7 @@ class MapSpace(object):
     def grad_list(self):
         if "grad_list" not in self._cache:
             _P.full_gradient(self.space)                        # tiles the stages have not asked for yet
-        return self._host("grad_list", self.space.grad4, lambda a: a[..., :3])
+        return self._host("grad_list", self.space.grad4[:self.space.n_oct], lambda a: a[..., :3])
 
     @property
     def rgi_space(self):

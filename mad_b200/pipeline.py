@@ -144,6 +144,7 @@ class Space(object):
         self.grad4 = []      # grad_list as float4  f32 [x][y][z][4]
         self.grad_flags = [] # per octave: None = the whole field is computed; else uint8 tile flags (mad_gradient_masked)
         self.dims = []
+        self.n_oct = 2       # 1 for oct_mode "up" / "base": octave slot 1 is a dummy the kernels never touch
         self.n_input_voxels = 0
         self._gauss = []     # Gaussian grids kept while tiles of the gradient may still be requested
         self._grad_done = {}  # (id(keypoint table object), radius) -> that object (kept alive: ids stay unique)
@@ -164,7 +165,7 @@ def gradient_reach(radius):
 
 def ensure_gradient(space, kp, radius=8):
     """Computes the gradient tiles within reach of the keypoints ``kp`` (no-op for a fully computed field)."""
-    if all(f is None for f in space.grad_flags) or len(kp) == 0:
+    if all(f is None for f in space.grad_flags[:space.n_oct]) or len(kp) == 0:
         return
     key = (id(kp), int(radius))
     if key in space._grad_done:
@@ -175,7 +176,7 @@ def ensure_gradient(space, kp, radius=8):
     if f0 is None or f1 is None:
         raise _lib.MadError("ensure_gradient: octaves must share the gradient mode")
     call("mad_gradient_mark", _ptr(kp.table), len(kp), _dptr(space.dims_host), up, base, _ptr(f0), _ptr(f1), st)
-    for o, (gx, gy, gz) in enumerate(space.dims):
+    for o, (gx, gy, gz) in enumerate(space.dims[:space.n_oct]):
         call("mad_gradient_masked", _ptr(space._gauss[o]), gx, gy, gz, _ptr(space.grad4[o]), _ptr(space.grad_flags[o]), st)
     space._grad_done[key] = kp
 
@@ -183,18 +184,23 @@ def ensure_gradient(space, kp, radius=8):
 def full_gradient(space):
     """Materialises the whole gradient field (``MapSpace.grad_list``): every tile not computed yet is requested."""
     st = _stream()
-    for o, (gx, gy, gz) in enumerate(space.dims):
+    for o, (gx, gy, gz) in enumerate(space.dims[:space.n_oct]):
         fl = space.grad_flags[o]
         if fl is None:
             continue
         fl[fl == 0] = 1
         call("mad_gradient_masked", _ptr(space._gauss[o]), gx, gy, gz, _ptr(space.grad4[o]), _ptr(fl), st)
         space.grad_flags[o] = None
+    space.grad_flags = [None] * len(space.grad_flags)           # (a single-octave space's dummy slot follows)
     return space.grad4
 
 
-def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True, keep_gauss=True, full_gradient=True):
+def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True, keep_gauss=True, full_gradient=True,
+                oct_mode="both"):
     """a1-a4.  ``grid``: float32 [x][y][z], torch CUDA tensor or NumPy array (copied to the device).
+    oct_mode (mad/MapSpace.py:149-163): "both" = [up, base]; "up" / "base" = that grid alone AS OCTAVE 0 -- the later
+    stages pick their patch geometry from the octave index (mad/Orientator.py:125, mad/Descriptor.py:131), so a lone base
+    grid is sampled with the stride-2 patches of octave 0, exactly as the reference does.
     full_gradient=False: the gradient field is computed later, only on the tiles the keypoints' patches touch
     (``ensure_gradient``, called by ``orient`` / ``describe``) or on demand (``full_gradient``)."""
     _require_cuda()
@@ -213,20 +219,28 @@ def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True
     else:
         bx, by, bz = nx, ny, nz
         base = grid
+    if oct_mode not in ("both", "up", "base"):
+        raise _lib.MadError("build_space: oct_mode %r" % (oct_mode,))
     # a2: 2x upsampled octave
     ux, uy, uz = 2 * bx - 1, 2 * by - 1, 2 * bz - 1
-    up = torch.empty((ux, uy, uz), dtype=torch.float32, device=dev)
-    ws_bytes = _lib.lib.mad_upsample_workspace_bytes(bx, by, bz)
-    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-    if sig_presmooth:
-        rad = tables.gaussian_radius(sig_presmooth)
-        gw = np.ascontiguousarray(tables.gaussian_weights(sig_presmooth, 0, rad))
-        call("mad_upsample_presmooth", _ptr(base), bx, by, bz, _dptr(gw), rad, _ptr(up), _ptr(ws), ws_bytes, st)
+    if oct_mode != "base":
+        up = torch.empty((ux, uy, uz), dtype=torch.float32, device=dev)
+        ws_bytes = _lib.lib.mad_upsample_workspace_bytes(bx, by, bz)
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        if sig_presmooth:
+            rad = tables.gaussian_radius(sig_presmooth)
+            gw = np.ascontiguousarray(tables.gaussian_weights(sig_presmooth, 0, rad))
+            call("mad_upsample_presmooth", _ptr(base), bx, by, bz, _dptr(gw), rad, _ptr(up), _ptr(ws), ws_bytes, st)
+        else:
+            call("mad_upsample_presmooth", _ptr(base), bx, by, bz, C.c_void_p(0), 0, _ptr(up), _ptr(ws), ws_bytes, st)
+        del ws
+    if oct_mode == "both":
+        sp.grids = [up, base]
+        sp.dims = [(ux, uy, uz), (bx, by, bz)]
     else:
-        call("mad_upsample_presmooth", _ptr(base), bx, by, bz, C.c_void_p(0), 0, _ptr(up), _ptr(ws), ws_bytes, st)
-    del ws
-    sp.grids = [up, base]
-    sp.dims = [(ux, uy, uz), (bx, by, bz)]
+        sp.n_oct = 1
+        sp.grids = [up] if oct_mode == "up" else [base]
+        sp.dims = [(ux, uy, uz) if oct_mode == "up" else (bx, by, bz)]
     # a3/a4 per octave
     rad = tables.gaussian_radius(sig_init)
     w0 = np.ascontiguousarray(tables.gaussian_weights(sig_init, 0, rad))
@@ -252,6 +266,10 @@ def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, exact_f64=True
         sp.grad4.append(gr)
     if full_gradient and not keep_gauss:
         sp._gauss = []
+    if sp.n_oct == 1:                                        # dummy octave 1: never indexed (no keypoint carries octave 1)
+        sp.dims.append((1, 1, 1))
+        sp.grad4.append(torch.zeros((1, 1, 1, 4), dtype=torch.float32, device=dev))
+        sp.grad_flags.append(None if full_gradient else torch.zeros(1, dtype=torch.uint8, device=dev))
     return sp
 
 
@@ -290,7 +308,7 @@ def detect(space, border=12, threshold=5e-2, cap=None):
     while True:
         cand = torch.empty((cap, 12), dtype=torch.int32, device=dev)
         counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        for o, (lg, (gx, gy, gz)) in enumerate(zip(space.logs, space.dims)):
+        for o, (lg, (gx, gy, gz)) in enumerate(zip(space.logs, space.dims)):      # (logs has n_oct entries)
             call("mad_detect", _ptr(lg), gx, gy, gz, o, int(border), C.c_float(threshold), _ptr(cand), cap,
                  _ptr(counter), st)
         n = _Readback.read(counter)[0]

@@ -80,7 +80,7 @@ def dense_record(out, key, arr, seed):
     out[key + "_absmax"] = np.array(float(np.abs(arr).max()))
 
 
-def run_pipeline(mrc_path, patch_size=16, want_hist=False):
+def run_pipeline(mrc_path, patch_size=16, want_hist=False, oct_mode="both"):
     from mad.MapSpace import MapSpace
     from mad.Detector import Detector
     from mad.Orientator import Orientator
@@ -88,7 +88,7 @@ def run_pipeline(mrc_path, patch_size=16, want_hist=False):
     Orientator.step1_reject = 0   # latent AttributeError, mad/Orientator.py:133,153
 
     t = {}
-    ms = MapSpace(mrc_path)
+    ms = MapSpace(mrc_path, oct_mode=oct_mode)
     t0 = time.perf_counter(); ms.build_space(); t["build_space"] = time.perf_counter() - t0
     t0 = time.perf_counter(); anchors = Detector().find_anchors(ms); t["find_anchors"] = time.perf_counter() - t0
     ori = Orientator(ori_radius=patch_size)
@@ -394,6 +394,28 @@ def main(which):
         out["pdb_rmsd"] = np.array([pa.get_rmsd_with(pb), pa.get_rmsdCA_with(pb)], dtype=np.float64)
         np.savez_compressed(os.path.join(GOLD, "score.npz"), **out)
         print("wrote score.npz", {k: (v.shape if v.ndim else float(v)) for k, v in out.items() if k != "pdb_text"})
+    if "octmode" in which:
+        # oct_mode "up" / "base" (mad/MapSpace.py:149-163; never selected by MaD.run): sparse results on the `small` input
+        with np.load(os.path.join(GOLD, "small.npz"), allow_pickle=False) as z:
+            q, voxelsp, origin = z["input_q"], float(z["voxelsp"]), tuple(z["origin"])
+        mrc_path = os.path.join(WORK, "octmode.mrc")
+        ref_shims.write_mrc_stub(mrc_path, synth.dequantise_u16(q), voxelsp, origin)
+        out = {}
+        for mode in ("up", "base"):
+            ms, anchors, described, t = run_pipeline(mrc_path, oct_mode=mode)
+            out[mode + "_voxelsp_list"] = np.array(ms.voxelsp_list, dtype=np.float64)
+            out[mode + "_n_grids"] = np.array(len(ms.map_space))
+            out[mode + "_log_sha256_flushed"] = np.array(sha_flushed(ms.map_space[0]))
+            out[mode + "_kp_oct"] = np.array([a.oct_scale for a in anchors], dtype=np.int32)
+            out[mode + "_kp_coords"] = np.array([a.coords for a in anchors], dtype=np.int32).reshape(-1, 3)
+            out[mode + "_kp_subv_map_coords"] = np.array([a.subv_map_coords for a in anchors], dtype=np.float64).reshape(-1, 3)
+            out[mode + "_of_index"] = np.array([d.index for d in described], dtype=np.int32)
+            out[mode + "_of_main"] = np.array([d.main_bin for d in described], dtype=np.int32)
+            out[mode + "_of_sec"] = np.array([d.sec_bin for d in described], dtype=np.int32)
+            dsc = np.array([d.lin_ar_subeqsp for d in described], dtype=np.int16).reshape(-1, 1024)
+            out[mode + "_dsc_crc32"] = np.array([zlib.crc32(r.tobytes()) for r in dsc], dtype=np.uint32)
+            print("octmode", mode, "K=%d D=%d" % (len(anchors), len(described)))
+        np.savez_compressed(os.path.join(GOLD, "octmode.npz"), **out)
     if "c1" in which:
         case_from_atoms("c1", synth.random_walk_atoms(9000, 85.0, 1), 4.0, 1.0, full_dsc=False)
 

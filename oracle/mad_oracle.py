@@ -101,8 +101,9 @@ def upsample2(grid):
     return a
 
 
-def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1):
-    """Returns dict(grid_list, map_space, gauss_list, grad_list) for oct_mode='both'."""
+def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1, oct_mode="both"):
+    """Returns dict(grid_list, map_space, gauss_list, grad_list); oct_mode as mad/MapSpace.py:149-163 ("up" / "base": that
+    grid alone, as octave 0)."""
     grid = np.asarray(grid, dtype=np.float32)
     if map_padding:
         grid = np.pad(grid, map_padding, mode="constant")                      # :118
@@ -110,7 +111,7 @@ def build_space(grid, map_padding=9, sig_init=2, sig_presmooth=1):
     if sig_presmooth:
         up = ndi.gaussian_filter(up, sigma=sig_presmooth)                      # :144
     up = up.astype(np.float32)
-    grids = [up, grid]
+    grids = {"both": [up, grid], "up": [up], "base": [grid]}[oct_mode]
     out = dict(grid_list=grids, map_space=[], gauss_list=[], grad_list=[])
     for g in grids:
         log_g = -1 * ndi.gaussian_laplace(g, sigma=sig_init) * sig_init ** 2   # :171

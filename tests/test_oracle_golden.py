@@ -8,6 +8,7 @@ import pytest
 
 import helpers as H
 import mad_oracle as mo
+import synth
 
 
 @pytest.mark.parametrize("case", ["tiny", "small", "pair_hi"])
@@ -126,3 +127,23 @@ def test_oracle_match_dsc_loop_equals_reference():
     assert res.shape == gm["results"].shape
     assert np.array_equal(res[:, 1:14], gm["results"][:, 1:14])            # repeatability, indices, coordinates
     assert np.abs(res[:, 0] - gm["results"][:, 0]).max() < 1e-14 and np.abs(res[:, 14:] - gm["results"][:, 14:]).max() < 1e-14
+
+
+@pytest.mark.parametrize("mode", ["up", "base"])
+def test_oracle_single_octave_modes_equal_reference(mode):
+    """oct_mode "up" / "base" (mad/MapSpace.py:149-163): the lone grid is octave 0, so the later stages sample it with the
+    stride-2 patch geometry of octave 0 -- keypoints, triples and descriptors against the reference's own run."""
+    g, gs = H.golden("octmode"), H.golden("small")
+    grid = synth.dequantise_u16(gs["input_q"])
+    sp = mo.build_space(grid, oct_mode=mode)
+    assert len(sp["map_space"]) == int(g[mode + "_n_grids"]) == 1
+    assert H.sha_flushed(sp["map_space"][0]) == str(g[mode + "_log_sha256_flushed"])
+    v = float(gs["voxelsp"])
+    org = np.asarray(gs["origin"], dtype=np.float64) - 9 * v
+    kp = mo.detect(sp["map_space"], list(g[mode + "_voxelsp_list"]), org)
+    assert np.array_equal(kp["coords"], g[mode + "_kp_coords"]) and np.array_equal(kp["oct"], g[mode + "_kp_oct"])
+    ori, tab = mo.orient(sp["grad_list"], kp)
+    assert np.array_equal(ori["kp"], g[mode + "_of_index"]) and np.array_equal(ori["main"], g[mode + "_of_main"])
+    assert np.array_equal(ori["sec"], g[mode + "_of_sec"])
+    dsc = mo.describe(sp["grad_list"], kp, ori, tab)
+    assert np.array_equal(H.crc_rows(dsc), g[mode + "_dsc_crc32"])

@@ -92,3 +92,35 @@ def test_mapspace_pdb_mode_runs_on_the_device(tmp_path):
     base = ms.grid_list[1][9:-9, 9:-9, 9:-9]
     assert np.abs(base - ref).max() <= 1.2e-7
     assert len(Detector().find_anchors(ms)) > 0
+
+
+@pytest.mark.parametrize("mode", ["up", "base"])
+def test_single_octave_modes_equal_reference(tmp_path, mode):
+    """MapSpace(oct_mode="up" / "base") (mad/MapSpace.py:149-163) through the reference-shaped classes against the
+    reference's own run: one grid, octave index 0, stride-2 patch geometry."""
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    import synth
+    from mad_b200 import mrc
+    from mad_b200.MapSpace import MapSpace
+    from mad_b200.Detector import Detector
+    from mad_b200.Orientator import Orientator
+    from mad_b200.Descriptor import Descriptor
+    g, gs = H.golden("octmode"), H.golden("small")
+    grid = synth.dequantise_u16(gs["input_q"])
+    path = os.path.join(str(tmp_path), "small.mrc")
+    mrc.write_mrc(path, grid.transpose(2, 1, 0), float(gs["voxelsp"]), origin=tuple(gs["origin"]))
+    ms = MapSpace(path, oct_mode=mode)
+    ms.build_space()
+    assert len(ms.map_space) == len(ms.grad_list) == len(ms.voxelsp_list) == 1
+    assert np.allclose(ms.voxelsp_list, g[mode + "_voxelsp_list"])
+    assert H.sha_flushed(ms.map_space[0]) == str(g[mode + "_log_sha256_flushed"])
+    anchors = Detector().find_anchors(ms)
+    assert np.array_equal(np.array([a.coords for a in anchors]).reshape(-1, 3), g[mode + "_kp_coords"])
+    assert all(a.oct_scale == 0 for a in anchors)
+    assert np.abs(np.array([a.subv_map_coords for a in anchors]).reshape(-1, 3) - g[mode + "_kp_subv_map_coords"]).max() <= 1e-6
+    described = Descriptor(dsc_radius=16).generate_descriptors(ms, Orientator(ori_radius=16).assign_orientations(ms, anchors))
+    assert np.array_equal([d.index for d in described], g[mode + "_of_index"])
+    assert np.array_equal([d.main_bin for d in described], g[mode + "_of_main"]) and np.array_equal([d.sec_bin for d in described], g[mode + "_of_sec"])
+    d = np.array([f.lin_ar_subeqsp for f in described], dtype=np.int16).reshape(-1, 1024)
+    assert np.array_equal(H.crc_rows(d), g[mode + "_dsc_crc32"])
