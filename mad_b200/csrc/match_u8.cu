@@ -194,6 +194,7 @@ struct U8Args {
     unsigned long long* count;    // device counter (hits found, may exceed cap)
     // TOPK
     int k, lo_index_base;
+    int local_tiles;              // TOP8: tiles at the start of a sweep handled by the epilogue threads themselves
     int dbg;                      // MAD_TOPK_DBG (measurement only): 1 = drain consumes without inserting, 2 = epilogue stages nothing
     int32_t* topk_idx;            // [2 S][M][k]: one list per (segment, epilogue group)
     double* topk_score;
@@ -769,7 +770,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         };
         int t = t_first;
         if (MODE == MODE_TOP8) {
-            for (int n = 0; n < TOP_LOCAL_TILES && t < t_end; ++n, t += kStep, it += kStep, par ^= 1) tile_body(std::true_type{}, t, it, par);
+            for (int n = 0; n < a.local_tiles && t < t_end; ++n, t += kStep, it += kStep, par ^= 1) tile_body(std::true_type{}, t, it, par);
             flush_local();
         }
         for (; t < t_end; t += kStep, it += kStep, par ^= 1) tile_body(std::false_type{}, t, it, par);
@@ -967,6 +968,7 @@ int mad_match_u8_topk(const void* hi_u8, int M, int M_pad, const void* lo_u8, in
     a.tiles_per_seg = (int)mad_ceil_div(mad_ceil_div(N, BN * ncta), S);
     a.hi_n2 = hi_n2; a.lo_n2 = lo_n2; a.lo_rnorm = lo_rnorm; a.cc = 0.0;
     a.k = k; a.lo_index_base = lo_index_base; a.topk_idx = topk_idx; a.topk_score = topk_score;
+    a.local_tiles = getenv("MAD_TOPK_LOCAL") ? atoi(getenv("MAD_TOPK_LOCAL")) : TOP_LOCAL_TILES;
     a.dbg = getenv("MAD_TOPK_DBG") ? atoi(getenv("MAD_TOPK_DBG")) : 0;
     if (a.dbg & 32) {
         unsigned long long z[8] = {0};

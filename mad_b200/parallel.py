@@ -39,11 +39,15 @@ def gather_topk(idx_local, score_local, group=None):
     g = _world(group)
     if g == 1:
         return idx_local[None], score_local[None]
-    idx_all = [torch.empty_like(idx_local) for _ in range(g)]
-    sc_all = [torch.empty_like(score_local) for _ in range(g)]
-    dist.all_gather(idx_all, idx_local.contiguous(), group=group)
-    dist.all_gather(sc_all, score_local.contiguous(), group=group)
-    return torch.stack(idx_all), torch.stack(sc_all)
+    idx_g = torch.empty((g,) + tuple(idx_local.shape), dtype=idx_local.dtype, device=idx_local.device)
+    sc_g = torch.empty((g,) + tuple(score_local.shape), dtype=score_local.dtype, device=score_local.device)
+    try:                                                    # straight into the [G, M, k] buffers the merge kernel reads
+        dist.all_gather_into_tensor(idx_g, idx_local.contiguous(), group=group)
+        dist.all_gather_into_tensor(sc_g, score_local.contiguous(), group=group)
+    except (RuntimeError, NotImplementedError):             # a backend without the tensor form
+        dist.all_gather(list(idx_g.unbind(0)), idx_local.contiguous(), group=group)
+        dist.all_gather(list(sc_g.unbind(0)), score_local.contiguous(), group=group)
+    return idx_g, sc_g
 
 
 def gather_varlen(t, group=None):

@@ -6,9 +6,9 @@ import sys
 
 MAP = [("pad3d_kernel", "pad3d_kernel"), ("spline_up_z_kernel", "spline_up_z_kernel"),
        ("spline_up_strided_kernel<double, double", "spline_up_x_kernel"), ("spline_up_strided_kernel<double, float", "spline_up_y_kernel"),
-       ("log_pass_strided_kernel", None), ("log_pass_z_kernel", "log_pass_z_kernel"), ("log_pass_yz_kernel", "log_pass_yz_kernel"), ("gradient_kernel", "gradient_kernel"),
+       ("log_pass_strided_kernel", None), ("log_pass_z_kernel", "log_pass_z_kernel"), ("log_pass_yz_kernel", "log_pass_yz_kernel"), ("gradient_masked_kernel", "gradient_masked_kernel"), ("gradient_kernel", "gradient_kernel"),
        ("detect_peaks_kernel", "detect_peaks_kernel"), ("orient_kernel", "orient_kernel"), ("describe_kernel", "describe_kernel"),
-       ("match_u8_kernel", "match_u8_pairs_kernel")]
+       ("match_u8_kernel<0", "match_u8_pairs_kernel"), ("match_u8_kernel<2", "match_u8_topk_kernel")]
 rows = list(csv.reader(open(sys.argv[1])))
 hdr, units, data = rows[0], rows[1], rows[2:]
 col = {h: i for i, h in enumerate(hdr)}

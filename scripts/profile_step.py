@@ -13,12 +13,10 @@ from mad_b200 import pipeline as P  # noqa: E402
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 do_match = int(sys.argv[2]) if len(sys.argv) > 2 else 1
-cache = "/tmp/mad_c2_%d.npy" % n
-if os.path.exists(cache):
-    grid = np.load(cache)
+if n == 256:
+    grid = synth.c2_inputs(0)[0]                      # the bench's C2 map
 else:
-    grid = synth.assembly_map(n, 8.0, 2.0, 6, 40000 if n >= 256 else 5000, 10)
-    np.save(cache, grid)
+    grid = synth.assembly_map(n, 8.0, 2.0, 6, 5000, 10)
 g = torch.from_numpy(grid).cuda()
 
 
