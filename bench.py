@@ -502,36 +502,28 @@ def bench_c5(ctx, args):
     M = N = int(os.environ.get("MAD_C5_ROWS", "100000"))
     k = 8
     hi_h, lo_h = synth.c5_descriptor_sets(M, N)                # identical inputs on every rank (same seeds)
-    s, e = par.shard_bounds(N, world)[rank]
-    hi_pin = torch.from_numpy(hi_h).pin_memory()
+    # rank grid: the reference (lo) axis is always cut; for larger worlds part of the factor goes to the hi axis, because
+    # cutting lo alone leaves every rank with all 782 CTAs and their fixed start-up (parallel.pick_topk_grid)
+    grid = tuple(int(x) for x in os.environ["MAD_C5_GRID"].split("x")) if "MAD_C5_GRID" in os.environ else par.pick_topk_grid(M, N, world)
+    gh, gl = grid
+    bh, bl = par.grid_coords(rank, gh, gl)
+    hs, he = par.shard_bounds(M, gh)[bh]
+    s, e = par.shard_bounds(N, gl)[bl]
+    hi_pin = torch.from_numpy(np.ascontiguousarray(hi_h[hs:he])).pin_memory()
     lo_pin = torch.from_numpy(np.ascontiguousarray(lo_h[s:e])).pin_memory()
     hi = P.DescriptorSet(hi_pin.to(dev))
     lo = P.DescriptorSet(lo_pin.to(dev))
     stage = P.HostStage()
-    # e2e: every rank needs ALL hi rows, but only 1 / world of them cross its PCIe link: the rank uploads its share and the
-    # shares are all-gathered over NVLink (as int32 words: NCCL has no int16)
-    hs, he = par.shard_bounds(M, world)[rank]
-    hi_share_pin = torch.from_numpy(np.ascontiguousarray(hi_h[hs:he])).pin_memory()
-    share_rows = max(b - a_ for a_, b in par.shard_bounds(M, world))
-    hi_share_up = torch.zeros((share_rows, 1024), dtype=torch.int16, device=dev)
-    hi_all_up = torch.empty((world * share_rows, 1024), dtype=torch.int16, device=dev)
+    hi_up = torch.empty(tuple(hi_pin.shape), dtype=torch.int16, device=dev)
     lo_up = torch.empty(tuple(lo_pin.shape), dtype=torch.int16, device=dev)
 
     def step_device():
-        return par.match_topk_sharded(hi, lo, k, s)
+        return par.match_topk_grid_sets(hi, lo, k, M, s, grid)
 
-    def step_e2e():
-        hi_share_up[: he - hs].copy_(hi_share_pin, non_blocking=True)
+    def step_e2e():                                             # per rank: its hi block and its lo shard over PCIe
+        hi_up.copy_(hi_pin, non_blocking=True)
         lo_up.copy_(lo_pin, non_blocking=True)
-        if world > 1:
-            ctx.dist.all_gather_into_tensor(hi_all_up.view(torch.int32), hi_share_up.view(torch.int32))
-            if M % world:                                   # ragged shares: drop each share's padding rows
-                hi_rows = torch.cat([hi_all_up[r * share_rows: r * share_rows + (b - a_)] for r, (a_, b) in enumerate(par.shard_bounds(M, world))])
-            else:
-                hi_rows = hi_all_up
-        else:
-            hi_rows = hi_share_up
-        idx, sc = par.match_topk_sharded(P.DescriptorSet(hi_rows), P.DescriptorSet(lo_up), k, s)
+        idx, sc = par.match_topk_grid_sets(P.DescriptorSet(hi_up), P.DescriptorSet(lo_up), k, M, s, grid)
         out = [stage.fetch("idx", idx), stage.fetch("sc", sc)]
         stage.sync()
         return out
@@ -542,11 +534,12 @@ def bench_c5(ctx, args):
     # ---- parity inside the run: sampled hi rows against the whole lo set on ONE GPU (the same kernel, unsharded)
     verified = None
     if world > 1:
-        rows = torch.from_numpy(np.sort(np.random.default_rng(5).choice(M, size=2048, replace=False))).to(dev)
+        rows = np.sort(np.random.default_rng(5).choice(M, size=2048, replace=False))
         full = P.DescriptorSet(torch.from_numpy(lo_h).to(dev))
-        sub = P.DescriptorSet(hi.dsc[rows].contiguous())
+        sub = P.DescriptorSet(torch.from_numpy(np.ascontiguousarray(hi_h[rows])).to(dev))
         i1, s1 = P.match_topk(sub, full, k)
-        verified = ctx.all_true(torch.equal(i1, idx[rows]) and torch.equal(s1, sc[rows]))
+        rows_d = torch.from_numpy(rows).to(dev)
+        verified = ctx.all_true(torch.equal(i1, idx[rows_d]) and torch.equal(s1, sc[rows_d]))
         del full, sub
     P.profile_enable(True)
     l0 = P.launch_count()
@@ -563,21 +556,23 @@ def bench_c5(ctx, args):
     (avg,) = ctx.max_over_ranks(avg)
     if rank != 0:
         return None
-    ops = 2.0 * M * (e - s) * 1024
+    ops = 2.0 * (he - hs) * (e - s) * 1024
     step_ms = ms / steps
     res = {
         "metric": "descriptor matches/sec (all-pairs cosine + top-8)", "value": M * N / (step_ms * 1e-3), "unit": "pairs/s",
         "n_gpus": world, "steps": steps, "ms_per_step": step_ms, "scaling": "strong",
-        "config": {"workload": "C5: %d x %d int16[1024] descriptors, top-%d, lo axis sharded over %d GPU(s), NCCL all_gather of "
-                               "[M, k] lists + k-way merge" % (M, N, k, world),
-                   "l2": "operands %.0f MB per rank > 126 MB L2" % ((M + e - s) * 1024 / 1e6)},
+        "config": {"workload": "C5: %d x %d int16[1024] descriptors, top-%d, rank grid %d hi blocks x %d lo (reference-axis) shards, NCCL "
+                               "all_gather of the per-rank [rows, k] lists + k-way merge over the lo shards" % (M, N, k, gh, gl),
+                   "grid": {"hi_blocks": gh, "lo_shards": gl},
+                   "l2": "operands %.0f MB per rank > 126 MB L2" % ((he - hs + e - s) * 1024 / 1e6)},
         "e2e": {"value": M * N / (ms_e2e / steps * 1e-3), "unit": "pairs/s",
-                "h2d_bytes_per_step": int(hi_share_pin.numel() * 2 + lo_pin.numel() * 2), "d2h_bytes_per_step": d2h,
-                "note": "per rank: 1 / n_gpus of the hi rows + its lo shard over PCIe; hi shares all-gathered over NVLink",
+                "h2d_bytes_per_step": int(hi_pin.numel() * 2 + lo_pin.numel() * 2), "d2h_bytes_per_step": d2h,
+                "note": "per rank: its hi block and its lo shard over PCIe, the merged [M, k] lists back",
                 "ms_per_step": ms_e2e / steps},
         "gpu_launches": int(launches),
         "roofline": {"bound": "tensor", "kernel": "match_u8_topk_kernel", "achieved": ops / (avg * 1e-3) / 1e12,
-                     "peak": ctx.i8_peak, "unit": "TOP/s", "frac": ops / (avg * 1e-3) / 1e12 / ctx.i8_peak, "traffic": None,
+                     "peak": ctx.i8_peak, "unit": "TOP/s", "frac": ops / (avg * 1e-3) / 1e12 / ctx.i8_peak,
+                     "traffic": ctx.traffic.get("match_u8_topk_kernel") if world == 1 else None,
                      "peak_source": ctx.i8_src, "avg_launch_ms": avg, "ops_per_launch": ops},
         "verified_equal_to_1gpu": verified,
     }

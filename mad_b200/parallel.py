@@ -150,3 +150,93 @@ def collect_units(local_tables, n_units, group=None, like=None):
             offs += c
     assert all(o is not None for o in out) and len(local_tables) == len(assign_units(n_units, rank, g))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# 2-D rank grid for all-pairs top-k: hi row blocks x lo (reference-axis) shards
+# ---------------------------------------------------------------------------------------------------------------------
+def topk_grid_cost(m, n, gh, gl, sms=148, tile_us=2.07, cta_fixed_us=110.0):
+    """Model of one rank's matching launch on a (gh x gl) grid: CTA pairs own 256 hi rows and sweep the rank's lo shard in
+    256-column tiles; a launch costs waves x (tiles + fixed per-CTA work: hi-tile load, thread-local start-up tiles).
+    Constants measured on B200."""
+    rows, cols = -(-m // gh), -(-n // gl)
+    ctas = 2 * (-(-rows // 256))
+    waves = -(-ctas // sms)
+    return waves * ((-(-cols // 256)) * tile_us + cta_fixed_us)
+
+
+def pick_topk_grid(m, n, world, min_lo_shards=2):
+    """(hi blocks, lo shards) with hi blocks * lo shards == world that minimises the modelled launch time.  The lo
+    (reference) axis is what north_star shards; cutting it ALONE leaves every rank with all ceil(m / 256) CTA pairs, each
+    paying its fixed start-up for an ever shorter sweep, so for larger worlds part of the factor goes to the hi axis."""
+    best = None
+    for gl in range(1, world + 1):
+        if world % gl or (world > 1 and gl < min(min_lo_shards, world)):
+            continue                                          # the reference axis is always cut (both operands shrink per rank)
+        gh = world // gl
+        c = topk_grid_cost(m, n, gh, gl) + (5.0 if gl > 1 else 0.0)      # (a merge launch when the lo axis is cut)
+        if best is None or c < best[0] - 1e-9:
+            best = (c, gh, gl)
+    return best[1], best[2]
+
+
+def grid_coords(rank, gh, gl):
+    """rank -> (hi block, lo shard); ranks of one hi block are consecutive."""
+    return rank // gl, rank % gl
+
+
+def match_topk_grid(hi_block_set, lo_shard_set, k, m_total, grid, group=None, impl=None, local=None):
+    """Per hi row of the WHOLE hi set the k best rows of the WHOLE lo set, on a (gh x gl) rank grid: rank r holds hi block
+    r // gl (rows ``shard_bounds(m_total, gh)``) and lo shard r % gl.  Every rank computes its block x shard top-k with
+    global lo indices; ONE all_gather over the world brings all G lists to every rank; the gl lists of each hi block are
+    merged with the (score desc, index asc) rule and the blocks concatenated: ([m_total, k] idx, score), identical on every
+    rank and bit-identical to one GPU.  ``local`` = precomputed (idx, score) of this rank's block x shard."""
+    gh, gl = grid
+    g = _world(group)
+    assert gh * gl == g, "grid %r does not match the world size %d" % (grid, g)
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    bh, bl = grid_coords(rank, gh, gl)
+    from . import pipeline as P
+    if local is None:
+        raise ValueError("match_topk_grid: pass local=(idx, score) of this rank's block x shard, or call match_topk_grid_sets")
+    idx, sc = local
+    rows_max = max(e - s for s, e in shard_bounds(m_total, gh))
+    if idx.shape[0] < rows_max:                               # ragged blocks: pad to the longest (padding rows are dropped below)
+        pad = rows_max - idx.shape[0]
+        idx = torch.cat([idx, torch.full((pad, k), -1, dtype=idx.dtype, device=idx.device)])
+        sc = torch.cat([sc, torch.full((pad, k), float("-inf"), dtype=sc.dtype, device=sc.device)])
+    idx_g, sc_g = gather_topk(idx, sc, group)                 # [G, rows_max, k], rank-major = [gh][gl]
+    if gl > 1:
+        idx_g = idx_g.view(gh, gl, rows_max, k).permute(1, 0, 2, 3).contiguous().view(gl, gh * rows_max, k)
+        sc_g = sc_g.view(gh, gl, rows_max, k).permute(1, 0, 2, 3).contiguous().view(gl, gh * rows_max, k)
+        if idx_g.is_cuda:
+            mi, ms = P.topk_merge(idx_g, sc_g)
+        else:
+            mi, ms = _merge_lists_host(idx_g, sc_g)
+    else:
+        mi, ms = idx_g.view(gh * rows_max, k), sc_g.view(gh * rows_max, k)
+    if m_total % gh:                                          # drop the padding rows of the shorter blocks
+        keep = torch.cat([torch.arange(b * rows_max, b * rows_max + (e - s), device=mi.device) for b, (s, e) in enumerate(shard_bounds(m_total, gh))])
+        mi, ms = mi[keep], ms[keep]
+    return mi, ms
+
+
+def _merge_lists_host(idx_g, sc_g):
+    """(score desc, index asc) k-way merge of [G, M, k] lists on CPU tensors (gloo tests; the GPU path uses mad_topk_merge)."""
+    g, m, k = idx_g.shape
+    idx = idx_g.permute(1, 0, 2).reshape(m, g * k)
+    sc = sc_g.permute(1, 0, 2).reshape(m, g * k)
+    big = torch.iinfo(torch.int64).max
+    key_i = torch.where(idx < 0, torch.full_like(idx, big, dtype=torch.int64), idx.to(torch.int64))
+    order = torch.argsort(key_i, dim=1, stable=True)          # index asc first, then a STABLE sort by score desc
+    sc1, idx1 = torch.gather(sc, 1, order), torch.gather(idx, 1, order)
+    order2 = torch.argsort(-sc1, dim=1, stable=True)[:, :k]
+    return torch.gather(idx1, 1, order2), torch.gather(sc1, 1, order2)
+
+
+def match_topk_grid_sets(hi_block_set, lo_shard_set, k, m_total, lo_index_base, grid, group=None, impl=None):
+    """``match_topk_grid`` with the block x shard launch done here (GPU): ``hi_block_set`` / ``lo_shard_set`` are this rank's
+    DescriptorSets, ``lo_index_base`` the global row of the lo shard's first row."""
+    from . import pipeline as P
+    idx, sc = P.match_topk(hi_block_set, lo_shard_set, k, lo_index_base=lo_index_base, impl=impl)
+    return match_topk_grid(hi_block_set, lo_shard_set, k, m_total, grid, group=group, impl=impl, local=(idx, sc))

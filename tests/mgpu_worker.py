@@ -37,6 +37,17 @@ def main():
     idx1, sc1 = P.match_topk(hs, ls_full, k)
     idx, sc = par.match_topk_sharded(hs, ls, k, s)
     assert torch.equal(idx, idx1) and torch.equal(sc, sc1), "sharded top-k differs from the 1-GPU result"
+    # 2-D rank grid (hi blocks x lo shards), every factorisation of the world
+    for gl in range(1, world + 1):
+        if world % gl:
+            continue
+        grid = (world // gl, gl)
+        bh, bl = par.grid_coords(rank, *grid)
+        h0, h1 = par.shard_bounds(m, grid[0])[bh]
+        l0, l1 = par.shard_bounds(n, grid[1])[bl]
+        gi, gs = par.match_topk_grid_sets(P.DescriptorSet(np.ascontiguousarray(hi[h0:h1])), P.DescriptorSet(np.ascontiguousarray(lo[l0:l1])),
+                                          k, m, l0, grid)
+        assert torch.equal(gi, idx1) and torch.equal(gs, sc1), "rank grid %r top-k differs from the 1-GPU result" % (grid,)
     a = P.match_threshold(hs, ls_full, 0.55)
     b = par.match_threshold_sharded(hs, ls, 0.55, s)
     assert a[0].numel() > 1000

@@ -69,9 +69,33 @@ def _worker(rank, world, port, q):
         op, osc2 = mo.match_threshold(hi, lo, 0.3)
         ok_thr = bool(len(op) > 50 and np.array_equal(np.stack([got[0].numpy(), got[1].numpy()], 1), op)
                       and np.abs(got[2].numpy() - osc2).max() < 1e-14)
-        q.put((rank, ok_topk, ok_var, units, ok_thr))
+        # 2-D rank grid (hi blocks x lo shards): both 2-rank grids, local lists from the oracle, merged == unsharded
+        ok_grid = True
+        for grid in ((1, 2), (2, 1)):
+            bh, bl = par.grid_coords(rank, *grid)
+            hs, he = par.shard_bounds(len(hi), grid[0])[bh]
+            ls_, le_ = par.shard_bounds(len(lo), grid[1])[bl]
+            gi, gs = mo.match_topk(hi[hs:he], lo[ls_:le_], k)
+            gi = np.where(gi >= 0, gi + ls_, -1).astype(np.int32)
+            mi2, ms2 = par.match_topk_grid(None, None, k, len(hi), grid, local=(torch.from_numpy(gi), torch.from_numpy(gs)))
+            mi2, ms2 = mi2.numpy(), ms2.numpy()
+            ok_grid = ok_grid and bool(np.array_equal(ms2, osc) and np.array_equal(mi2[ms2 > osc[:, -1:]], oi[osc > osc[:, -1:]]))
+        q.put((rank, ok_topk, ok_var, units, ok_thr, ok_grid))
     finally:
         dist.destroy_process_group()
+
+
+def test_topk_grid_choice():
+    sys.path.insert(0, REPO)
+    from mad_b200 import parallel as par
+    assert par.pick_topk_grid(100000, 100000, 1) == (1, 1)
+    assert par.pick_topk_grid(100000, 100000, 2) == (1, 2)          # the reference axis is always cut
+    assert par.pick_topk_grid(100000, 100000, 4) == (2, 2)
+    assert par.pick_topk_grid(100000, 100000, 8) == (2, 4)
+    for w in (2, 4, 8):
+        gh, gl = par.pick_topk_grid(1000, 10 ** 6, w)
+        assert gh * gl == w and gl >= 2
+    assert [par.grid_coords(r, 2, 4) for r in (0, 3, 4, 7)] == [(0, 0), (0, 3), (1, 0), (1, 3)]
 
 
 def test_shard_bounds_and_unit_assignment():
@@ -103,3 +127,4 @@ def test_world_size_2_gloo_topk_merge_and_varlen_gather():
     assert all(r[2] for r in res), "variable-length gather returned wrong shapes / contents"
     assert res[0][3] == [0, 2, 4, 6] and res[1][3] == [1, 3, 5]
     assert all(r[4] for r in res), "sharded threshold pair lists, gathered and merged, differ from the unsharded oracle"
+    assert all(r[5] for r in res), "2-D rank grid top-k differs from the unsharded oracle"
