@@ -61,9 +61,13 @@ CPU_OF = 160             # oriented features of the crop that go through describ
 CPU_MATCH = (1024, 4096)  # hi x lo block of the matching lines
 
 
+CPU_PRESETS = {      # (crop side, keypoints, oriented features, hi rows of the matching block): ~12 / 6 / 3 s per step on 16 cores
+    "full": (CPU_CROP, CPU_KP, CPU_OF, CPU_MATCH[0]), "half": (64, 24, 80, 512), "quarter": (48, 12, 40, 256)}
+
+
 def _cpu_stage_worker(job):
     """One process: the five stages of the path on samples sized in the stage's own unit; returns seconds per unit."""
-    crop, voxelsp = job
+    crop, voxelsp, n_kp, n_of, n_hi = job
     import mad_oracle as mo
     pc = time.perf_counter
     t0 = pc()
@@ -73,25 +77,25 @@ def _cpu_stage_worker(job):
     t0 = pc()
     kp = mo.detect(sp["map_space"], [voxelsp / 2, voxelsp], np.zeros(3))
     t_detect = pc() - t0
-    nk = min(CPU_KP, len(kp["oct"]))
+    nk = min(n_kp, len(kp["oct"]))
     kp_s = {k: v[:nk] for k, v in kp.items()}
     t0 = pc()
     ori, tab = mo.orient(sp["grad_list"], kp_s)
     t_orient = pc() - t0
-    nf = min(CPU_OF, len(ori["kp"]))
+    nf = min(n_of, len(ori["kp"]))
     ori_s = {k: v[:nf] for k, v in ori.items()}
     t0 = pc()
     dsc = mo.describe(sp["grad_list"], kp_s, ori_s, tab)
     t_describe = pc() - t0
     rng = np.random.default_rng(0)
     base = dsc if len(dsc) else np.ones((1, 1024), dtype=np.int16)
-    hi = base[rng.integers(0, len(base), CPU_MATCH[0])]
+    hi = base[rng.integers(0, len(base), n_hi)]
     lo = base[rng.integers(0, len(base), CPU_MATCH[1])]
     t0 = pc()
     mo.match_threshold(hi, lo, 0.6)
     t_match = pc() - t0
     return dict(build_per_voxel=t_build / v1, detect_per_voxel=t_detect / v1, orient_per_kp=t_orient / max(nk, 1),
-                describe_per_feature=t_describe / max(nf, 1), match_per_pair=t_match / (CPU_MATCH[0] * CPU_MATCH[1]),
+                describe_per_feature=t_describe / max(nf, 1), match_per_pair=t_match / (n_hi * CPU_MATCH[1]),
                 crop_keypoints=int(len(kp["oct"])), seconds=t_build + t_detect + t_orient + t_describe + t_match)
 
 
@@ -109,7 +113,7 @@ def cpu_crops(grid, n_crops, side):
     return [np.ascontiguousarray(grid[x:x + side, y:y + side, z:z + side]) for _, x, y, z in cands[:n_crops]]
 
 
-def cpu_stage_sample(grid, voxelsp, procs, steps, warmup, v1_full, K=C2_K, D=C2_D, M=C2_M, n_vox=None):
+def cpu_stage_sample(grid, voxelsp, procs, steps, warmup, v1_full, K=C2_K, D=C2_D, M=C2_M, n_vox=None, preset="full"):
     """The reference's CPU path on the C2 map, sampled STAGE BY STAGE in each stage's own unit and scaled to the whole map:
     build_space + find_anchors per padded base voxel (an 80^3 occupancy-matched crop), assign_orientations per keypoint
     (48 keypoints of the crop), generate_descriptors per oriented feature (160 of them), the two matching lines per scored
@@ -119,10 +123,11 @@ def cpu_stage_sample(grid, voxelsp, procs, steps, warmup, v1_full, K=C2_K, D=C2_
     memory-bandwidth contention between the processes is inside the measurement.
     Returns (voxels/s of `procs` maps in flight, seconds per step, per-unit costs of the last step)."""
     import multiprocessing as mp
-    crops = cpu_crops(grid, procs, CPU_CROP)
+    side, n_kp, n_of, n_hi = CPU_PRESETS[preset]
+    crops = cpu_crops(grid, procs, side)
     while len(crops) < procs:
         crops.append(crops[len(crops) % max(len(crops), 1)])
-    jobs = [(c, voxelsp) for c in crops]
+    jobs = [(c, voxelsp, n_kp, n_of, n_hi) for c in crops]
     ctx = mp.get_context("fork")
     res = None
     with ctx.Pool(procs) as pool:
@@ -162,7 +167,12 @@ def run_reference(args):
     grid = synth.assembly_map(**C2)
     procs = host_procs()
     v1 = (C2["n"] + 18) ** 3
-    value, s_per_step, unit = cpu_stage_sample(grid, C2["voxelsp"], procs, args.steps, args.warmup, v1)
+    # the sample shrinks with the number of steps so that the whole run stays near three minutes (per-unit costs do not
+    # depend on the sample size, only their noise does)
+    per_step = 170.0 / max(1, args.steps + args.warmup)
+    preset = "full" if per_step >= 12.0 else ("half" if per_step >= 6.0 else "quarter")
+    value, s_per_step, unit = cpu_stage_sample(grid, C2["voxelsp"], procs, args.steps, args.warmup, v1, preset=preset)
+    unit["sample_preset"] = preset
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,

@@ -369,14 +369,13 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         for (int qq = 0; qq < 4; ++qq) hi_n2_reg[qq] = (m0 + qq * 32 + lane < a.M) ? __ldg(a.hi_n2 + m0 + qq * 32 + lane) : 0;
         for (long long spins = 0; spins < (1LL << 27); ++spins) {    // (bounded: a protocol error must not hang the device)
             int done = 0;
-            for (int e = e0; e < e0 + 4; ++e) done += s_done[e];
+            for (int e = e0; e < e0 + 4; ++e) done += mad_ld_acquire_cta(&s_done[e]);
             bool any = false;
             for (int e = e0; e < e0 + 4; ++e) {
                 for (int h = 0; h < 2; ++h) {
-                    const int n = s_half[2 * e + h];
+                    const int n = mad_ld_acquire_cta(&s_half[2 * e + h]);      // (acquire: the entries were written before the state word)
                     if (n <= 0) continue;
                     any = true;
-                    __threadfence_block();                           // the entries were written before the state word
                     const unsigned long long* hk = stg_key + e * STG + h * HALF;
                     const int* hd = stg_dot + e * STG + h * HALF;
                     unsigned long long ent[2];
@@ -389,7 +388,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
                         dot[k] = (i < n) ? hd[i] : 0;
                     }
                     __syncwarp();
-                    if (lane == 0) s_half[2 * e + h] = 0;            // the half may be refilled: its entries are in registers
+                    if (lane == 0) mad_st_release_cta(&s_half[2 * e + h], 0);   // the half may be refilled: its entries are in registers
                     int total = 0, pos[2];
                     const int qe = e & 3;
                     const int n2_q = qe == 0 ? hi_n2_reg[0] : (qe == 1 ? hi_n2_reg[1] : (qe == 2 ? hi_n2_reg[2] : hi_n2_reg[3]));
@@ -567,10 +566,9 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
             __syncwarp();
             if (n > 0) {
                 if (lane == 0) {
-                    __threadfence_block();
-                    s_half[2 * ew + cur] = n;
+                    mad_st_release_cta(&s_half[2 * ew + cur], n);    // (release; MEMBAR.SC.CTA of __threadfence_block is far heavier)
                     long long spins = 0;
-                    while (s_half[2 * ew + (cur ^ 1)] != 0 && ++spins < (1LL << 27)) __nanosleep(100);   // other half still in use
+                    while (mad_ld_acquire_cta(&s_half[2 * ew + (cur ^ 1)]) != 0 && ++spins < (1LL << 27)) __nanosleep(64);   // other half still in use
                     if (spins >= (1LL << 27)) atomicExch(a.count, MAD_MATCH_TIMEOUT_COUNT);              // fail loudly on the host
                 }
                 cur ^= 1;
@@ -777,7 +775,7 @@ match_u8_kernel(const __grid_constant__ CUtensorMap map_hi, const __grid_constan
         if (!kTop) {
             publish(stg_n);
             __syncwarp();
-            if (lane == 0) { __threadfence_block(); s_done[ew] = 1; }
+            if (lane == 0) mad_st_release_cta(&s_done[ew], 1);
         }
         if (MODE == MODE_TOP8) {
             __syncwarp();

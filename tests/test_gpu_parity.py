@@ -464,7 +464,6 @@ def test_map_stream_compact_format(P):
         got = P.scores_from_dots(out["pair_hi"].numpy(), out["pair_lo"].numpy(), out["pair_dot"].numpy(), hi.norm2.cpu().numpy(),
                                  out["lo_norm2"].numpy())
         assert np.array_equal(got, sc.cpu().numpy())
-    assert len(got) == len(H.golden("pair_match")["pairs"]) or True
 
 
 def test_c3_size_scale_space_linearity(P):
