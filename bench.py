@@ -429,9 +429,11 @@ def bench_c2(ctx, args):
             continue
         gbs = nbytes / (t_ms * 1e-3) / 1e9
         top = max(kns, key=lambda k: per_step.get(k, 0.0))
+        tr = ctx.traffic.get(top)
         per_stage[name] = {"ms": round(t_ms, 4), "algorithmic_bytes": int(nbytes), "achieved": round(gbs, 1), "unit": "GB/s",
-                           "frac": round(gbs / ctx.hbm_peak, 4), "dominant_kernel": top,
-                           "traffic": ctx.traffic.get(top)}
+                           "frac": round(gbs / ctx.hbm_peak, 4), "dominant_kernel": top, "traffic": tr,
+                           # the dominant kernel's OWN DRAM bytes (ncu) over its own time: how close it runs to the memory system
+                           "own_traffic_frac": round(tr / (per_step[top] * 1e-3) / 1e9 / ctx.hbm_peak, 4) if tr and per_step.get(top) else None}
     M_hi = hi_all.rows
     match_kernels = [k for k in per_step if "match" in k or "pairs" in k or k in ("cub_radix_sort_pairs", "dsc_prepare_kernel",
                                                                                   "publish_small_kernel", "zero_u64_kernel")]
