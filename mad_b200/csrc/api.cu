@@ -186,10 +186,51 @@ static int topk_lists(int M, int N, int k, int impl) {
     return impl == 0 ? u8_lists_per_segment(k) * mad_match_u8_segments_topk(M, N) : mad_match_segments(M, N, impl);
 }
 
-extern "C" size_t mad_match_topk_workspace_bytes(int M, int N, int k, int impl) {
+static size_t topk_part_workspace_bytes(int M, int N, int k, int impl) {
     const int S = topk_lists(M, N, k, impl);
     if (S <= 1 || M <= 0) return 256;
     return mad_align_up((size_t)S * M * k * sizeof(int32_t), 256) + mad_align_up((size_t)S * M * k * sizeof(double), 256);
+}
+
+// Rows of a poorly filled LAST WAVE of the uint8 top-8 kernel.  A CTA pair owns 256 hi rows and sweeps the whole lo set, so
+// 100 000 rows are 391 pairs = 5.28 waves of 74 and the last wave keeps 28 % of the machine busy for a full sweep.  When the
+// last wave is at most half full its rows get a launch of their own with the lo axis cut into segments (more, shorter CTAs):
+// 5 full waves + a short tail launch instead of 6 waves.
+static int topk_tail_rows(int M, int k, int impl) {
+    if (impl != 0 || k > 8 || getenv("MAD_TOPK_NO_TAIL")) return 0;
+    const int per_wave = mad_sm_count() / 2;
+    const int pairs = (int)mad_ceil_div(M, 256);
+    if (per_wave <= 0 || pairs <= per_wave) return 0;
+    const int tail = pairs % per_wave;
+    if (tail == 0 || 2 * tail > per_wave) return 0;
+    return M - (pairs - tail) * 256;
+}
+
+extern "C" size_t mad_match_topk_workspace_bytes(int M, int N, int k, int impl) {
+    const int tail = topk_tail_rows(M, k, impl);
+    if (tail <= 0) return topk_part_workspace_bytes(M, N, k, impl);
+    return std::max(topk_part_workspace_bytes(M - tail, N, k, impl), topk_part_workspace_bytes(tail, N, k, impl));
+}
+
+static int topk_part(const MadDscSet* hi, const MadDscSet* lo, int k, int lo_index_base, int32_t* topk_idx, double* topk_score,
+                     void* workspace, size_t workspace_bytes, int impl, cudaStream_t st) {
+    const int M = hi->rows;
+    const int S = topk_lists(M, lo->rows, k, impl);                // lists to merge
+    auto run_topk = [&](int lists, int32_t* oi, double* os) {
+        const int segs = impl == 0 ? lists / u8_lists_per_segment(k) : lists;
+        if (impl == 0)
+            return mad_match_u8_topk(hi->u8, hi->rows, hi->rows_padded, lo->u8, lo->rows, lo->rows_padded, hi->norm2,
+                                     lo->norm2, lo->rnorm, segs, k, lo_index_base, oi, os, st);
+        return run_match(hi, lo, 0.0, 2, segs, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, oi, os, impl, st);
+    };
+    if (S == 1) return run_topk(1, topk_idx, topk_score);
+    MAD_CHECK_ARG(workspace && workspace_bytes >= topk_part_workspace_bytes(M, lo->rows, k, impl));
+    int32_t* pidx = reinterpret_cast<int32_t*>(workspace);
+    double* pscore = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) +
+                                               mad_align_up((size_t)S * M * k * sizeof(int32_t), 256));
+    int rc = run_topk(S, pidx, pscore);
+    if (rc != MAD_OK) return rc;
+    return mad_topk_merge_launch(pidx, pscore, S, M, k, topk_idx, topk_score, st);
 }
 
 extern "C" int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, int lo_index_base, int32_t* topk_idx,
@@ -206,22 +247,23 @@ extern "C" int mad_match_topk(const MadDscSet* hi, const MadDscSet* lo, int k, i
         // -inf as float64 = 0xFFF0000000000000: written by the merge kernel over zero shards
         return mad_topk_merge_launch(topk_idx, topk_score, 0, M, k, topk_idx, topk_score, st);
     }
-    const int S = topk_lists(M, lo->rows, k, impl);                // lists to merge
-    auto run_topk = [&](int lists, int32_t* oi, double* os) {
-        const int segs = impl == 0 ? lists / u8_lists_per_segment(k) : lists;
-        if (impl == 0)
-            return mad_match_u8_topk(hi->u8, hi->rows, hi->rows_padded, lo->u8, lo->rows, lo->rows_padded, hi->norm2,
-                                     lo->norm2, lo->rnorm, segs, k, lo_index_base, oi, os, st);
-        return run_match(hi, lo, 0.0, 2, segs, nullptr, nullptr, nullptr, nullptr, nullptr, k, lo_index_base, oi, os, impl, st);
-    };
-    if (S == 1) return run_topk(1, topk_idx, topk_score);
-    MAD_CHECK_ARG(workspace && workspace_bytes >= mad_match_topk_workspace_bytes(M, lo->rows, k, impl));
-    int32_t* pidx = reinterpret_cast<int32_t*>(workspace);
-    double* pscore = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) +
-                                               mad_align_up((size_t)S * M * k * sizeof(int32_t), 256));
-    rc = run_topk(S, pidx, pscore);
+    const int tail = topk_tail_rows(M, k, impl);
+    if (tail <= 0) return topk_part(hi, lo, k, lo_index_base, topk_idx, topk_score, workspace, workspace_bytes, impl, st);
+    // two launches on the same stream (the workspace is reused in stream order): the full waves, then the tail rows
+    const int M0 = M - tail;                                       // a multiple of 256
+    MadDscSet a = *hi, b = *hi;
+    a.rows = M0;
+    a.rows_padded = M0;
+    b.rows = tail;
+    b.rows_padded = hi->rows_padded - M0;
+    b.dsc = hi->dsc ? hi->dsc + (size_t)M0 * MAD_DSC_LEN : nullptr;
+    b.u8 = hi->u8 ? hi->u8 + (size_t)M0 * MAD_DSC_LEN : nullptr;
+    b.norm2 = hi->norm2 + M0;
+    b.rnorm = hi->rnorm ? hi->rnorm + M0 : nullptr;
+    rc = topk_part(&a, lo, k, lo_index_base, topk_idx, topk_score, workspace, workspace_bytes, impl, st);
     if (rc != MAD_OK) return rc;
-    return mad_topk_merge_launch(pidx, pscore, S, M, k, topk_idx, topk_score, st);
+    return topk_part(&b, lo, k, lo_index_base, topk_idx + (size_t)M0 * k, topk_score + (size_t)M0 * k, workspace, workspace_bytes,
+                     impl, st);
 }
 
 // ---- small device -> host readbacks that do not use a copy engine -------------------------------------------------

@@ -847,12 +847,13 @@ int check_device() {
 
 }  // namespace
 
-// Number of lo segments: minimises  waves x (tiles per segment + 1)  -- one CTA per SM (224 KB of
-// shared memory), a CTA costs its lo tiles plus one tile-equivalent for loading the hi tile.
+// Number of lo segments: minimises  waves x (tiles per segment + fixed)  -- one CTA per SM (224 KB of shared memory).
 static int pick_ncta(int M, int N_pad);
 
+// fixed_tiles: what a CTA costs besides its lo tiles, in tile-equivalents (~2.07 us): loading the hi tile (1) and, in top-8
+// mode, the thread-local start-up tiles and the early staged phase (~110 us measured = 53).
 // slack > 1: the SMALLEST number of segments whose cost is within that factor of the best.
-static int u8_segments(int M, int N, double slack) {
+static int u8_segments(int M, int N, double slack, int fixed_tiles) {
     if (M <= 0 || N <= 0) return 1;
     const int tn = pick_ncta(M, 256) == 2 ? 2 * BN : BN;           // tile width of the variant this M gets
     const long long m_tiles = mad_ceil_div(M, BM);
@@ -863,7 +864,7 @@ static int u8_segments(int M, int N, double slack) {
         const long long per = mad_ceil_div(n_tiles, s);
         const long long segs = mad_ceil_div(n_tiles, per);      // no empty segments
         if (segs != s) return -1;
-        return mad_ceil_div(m_tiles * s, sms) * (per + 1);
+        return mad_ceil_div(m_tiles * s, sms) * (per + fixed_tiles);
     };
     for (long long s = 1; s <= n_tiles; ++s) {
         const long long cost = cost_of(s);
@@ -878,15 +879,15 @@ static int u8_segments(int M, int N, double slack) {
     return (int)best_s;
 }
 
-int mad_match_u8_segments(int M, int N) { return u8_segments(M, N, 1.0); }
+int mad_match_u8_segments(int M, int N) { return u8_segments(M, N, 1.0, 1); }
 
-// Top-k keeps one running list per (segment, epilogue group) and every list pays its own ~k ln(columns / k) insertions
-// (exact float64 score + insertion network, on the critical path of its tile): with the 11 segments the tile-cost model
-// picks for 100 000 x 100 000 rows the kernel spent 1107 candidate events per row instead of ~140 and ran at 37 % of the
-// tensor peak.  So top-k takes the fewest segments whose wave / tile cost is within 12 % of the best.
+// Top-8: every (segment, row) keeps its own lists and pays its own start-up (the first tiles of a sweep see 60 % of a
+// row's candidate events), so a CTA's fixed cost is ~53 tile-equivalents; with that in the model the sweep of 100 000 x
+// 100 000 rows stays in ONE segment, and the short launch over the rows of a poorly filled last wave (mad_match_topk)
+// gets 3.
 int mad_match_u8_segments_topk(int M, int N) {
-    static const double slack = getenv("MAD_TOPK_SLACK") ? atof(getenv("MAD_TOPK_SLACK")) : 1.12;
-    return u8_segments(M, N, slack);
+    static const int fixed = getenv("MAD_TOPK_FIXED_TILES") ? atoi(getenv("MAD_TOPK_FIXED_TILES")) : 53;
+    return u8_segments(M, N, 1.0, fixed);
 }
 
 // CTA pairs are used when there are at least two hi tiles (MAD_MATCH_ONE_CTA=1 forces the one-CTA kernel).

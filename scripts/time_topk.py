@@ -14,4 +14,4 @@ for _ in range(5): P.match_topk(hi, lo, 8)
 torch.cuda.synchronize()
 r = {}
 for nm, t in P.profile_records(): r.setdefault(nm, []).append(t)
-print("M=%d N=%d dbg=%s slack=%s " % (M, N, os.environ.get("MAD_TOPK_DBG"), os.environ.get("MAD_TOPK_SLACK")) + "  ".join("%s %.3f ms" % (k, np.mean(v)) for k, v in r.items()))
+print("M=%d N=%d dbg=%s slack=%s " % (M, N, os.environ.get("MAD_TOPK_DBG"), os.environ.get("MAD_TOPK_SLACK")) + "  ".join("%s %.3f ms per call (%d launches)" % (k, np.sum(v) / 5, len(v) // 5) for k, v in r.items()))
