@@ -91,7 +91,7 @@ def test_topk_grid_choice():
     assert par.pick_topk_grid(100000, 100000, 1) == (1, 1)
     assert par.pick_topk_grid(100000, 100000, 2) == (1, 2)          # the reference axis is always cut
     assert par.pick_topk_grid(100000, 100000, 4) == (2, 2)
-    assert par.pick_topk_grid(100000, 100000, 8) == (2, 4)
+    assert par.pick_topk_grid(100000, 100000, 8) == (4, 2)
     for w in (2, 4, 8):
         gh, gl = par.pick_topk_grid(1000, 10 ** 6, w)
         assert gh * gl == w and gl >= 2
