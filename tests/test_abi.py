@@ -72,3 +72,22 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(root, f)).read()
                 assert not re.search(r"^\s*(import|from)\s+(mad_oracle|synth|ref_shims|oracle)\b", src, flags=re.M), f
+
+
+def test_scores_from_dots_is_the_device_formula():
+    """pipeline.scores_from_dots (host side of the compact pair format) against the reference's own lines on unit rows
+    (mad/MaD.py:416-420): the exact integer dot over sqrt(n_hi n_lo) agrees with the float64 dgemm score to 1e-14, and zero
+    descriptors score 0."""
+    import numpy as np
+    import synth
+    import mad_oracle as mo
+    from mad_b200.pipeline import scores_from_dots
+    lo = synth.synthetic_descriptors(60, 3)
+    hi = synth.synthetic_descriptors(40, 4, noisy_copy_of=lo)
+    hi[3] = 0
+    ph, pl = np.meshgrid(np.arange(40), np.arange(60), indexing="ij")
+    ph, pl = ph.ravel(), pl.ravel()
+    dot = (hi.astype(np.int64) @ lo.astype(np.int64).T).ravel()
+    n_hi, n_lo = (hi.astype(np.int64) ** 2).sum(1), (lo.astype(np.int64) ** 2).sum(1)
+    got = scores_from_dots(ph, pl, dot, n_hi, n_lo).reshape(40, 60)
+    assert np.abs(got - mo.match_scores(hi, lo)).max() < 1e-14 and not got[3].any()

@@ -147,3 +147,18 @@ def test_oracle_single_octave_modes_equal_reference(mode):
     assert np.array_equal(ori["sec"], g[mode + "_of_sec"])
     dsc = mo.describe(sp["grad_list"], kp, ori, tab)
     assert np.array_equal(H.crc_rows(dsc), g[mode + "_dsc_crc32"])
+
+
+def test_oracle_port_equals_reference_on_a_benchmarked_snapshot():
+    """The port that `bench.py --impl reference` times, on config C4's snapshot 63 (one of the maps bench.py runs): same
+    keypoints, (index, main, sec) triples and descriptor rows as the UNMODIFIED reference (tests/golden/c4.npz)."""
+    g = H.golden("c4")
+    grid = synth.c4_snapshot(63)
+    assert H.sha(np.ascontiguousarray(grid, dtype=np.float32)) == str(g["s63_input_sha256"])
+    sp, kp, ori, dsc = mo.describe_struct(grid, 1.0)
+    assert np.array_equal(kp["coords"], g["s63_kp_coords"]) and np.array_equal(kp["oct"], g["s63_kp_oct"])
+    assert np.array_equal(ori["kp"], g["s63_of_index"]) and np.array_equal(ori["main"], g["s63_of_main"])
+    assert np.array_equal(ori["sec"], g["s63_of_sec"])
+    assert np.array_equal(H.crc_rows(dsc), g["s63_dsc_crc32"])
+    for key, a in (("log0", sp["map_space"][0]), ("log1", sp["map_space"][1]), ("up_grid", sp["grid_list"][0])):
+        assert H.sha_flushed(a) == str(g["s63_%s_sha256_flushed" % key]), key
