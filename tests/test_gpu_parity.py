@@ -359,6 +359,28 @@ def test_tcgen05_equals_simt_exactly(P):
         assert torch.equal(t0[0], t1[0]) and torch.equal(t0[1], t1[1])
 
 
+def test_topk_last_wave_split_equals_simt(P):
+    """mad_match_topk gives the rows of a poorly filled last wave (here 74 full CTA pairs + 300 rows) a second, segmented
+    launch: the stitched result must equal the SIMT integer kernel's bit for bit, and the unsplit launch's."""
+    import os
+    import synth
+    lo = synth.synthetic_descriptors(3000, 51)
+    m = 74 * 256 + 300
+    base = synth.synthetic_descriptors(2048, 52, noisy_copy_of=lo)
+    hi = np.concatenate([np.roll(base, 7 * r, axis=1) for r in range((m + 2047) // 2048)])[:m]
+    hi[m - 5] = 0
+    dh, dl = P.DescriptorSet(hi), P.DescriptorSet(lo)
+    a = P.match_topk(dh, dl, 8, lo_index_base=11, impl=0)
+    b = P.match_topk(dh, dl, 8, lo_index_base=11, impl=1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    os.environ["MAD_TOPK_NO_TAIL"] = "1"
+    try:
+        c = P.match_topk(dh, dl, 8, lo_index_base=11, impl=0)
+    finally:
+        del os.environ["MAD_TOPK_NO_TAIL"]
+    assert torch.equal(a[0], c[0]) and torch.equal(a[1], c[1])
+
+
 def test_onepass_candidate_overflow_and_dense_hits(P):
     """The one-pass matcher's candidate list: a too-small first buffer is repeated with room;
     very dense hits (a set against itself at a low threshold) overflow the per-warp staging and
