@@ -151,8 +151,8 @@ def cpu_stage_sample(grid, voxelsp, procs, steps, warmup, v1_full, K=C2_K, D=C2_
 CPU_SAMPLE_TEXT = ("stage-wise sample of the C2 map per process: build_space + find_anchors on an %d^3 occupancy-matched crop "
                    "(scaled per padded base voxel), assign_orientations on %d keypoints, generate_descriptors on %d oriented "
                    "features, the matching lines on a %d x %d block; scaled to the map's V1 = 274^3, K = %d, D = %d, M = %d; "
-                   "oracle/mad_oracle.py = vectorised NumPy/SciPy port, bit-exact with the reference on the fixtures and ~10x "
-                   "faster than it (the reference itself, one thread, took 374 s for this map in the build container)"
+                   "oracle/mad_oracle.py = vectorised NumPy/SciPy port, bit-exact with the reference on the fixtures and 1.5x "
+                   "faster than it (this map, one thread, build container: the reference 374 s, the port 253 s)"
                    % (CPU_CROP, CPU_KP, CPU_OF, CPU_MATCH[0], CPU_MATCH[1], C2_K, C2_D, C2_M))
 
 
