@@ -148,12 +148,17 @@ def cpu_stage_sample(grid, voxelsp, procs, steps, warmup, v1_full, K=C2_K, D=C2_
     return procs * (n_vox if n_vox else C2["n"] ** 3) / t_map, dt, unit
 
 
-CPU_SAMPLE_TEXT = ("stage-wise sample of the C2 map per process: build_space + find_anchors on an %d^3 occupancy-matched crop "
-                   "(scaled per padded base voxel), assign_orientations on %d keypoints, generate_descriptors on %d oriented "
-                   "features, the matching lines on a %d x %d block; scaled to the map's V1 = 274^3, K = %d, D = %d, M = %d; "
-                   "oracle/mad_oracle.py = vectorised NumPy/SciPy port, bit-exact with the reference on the fixtures and 1.5x "
-                   "faster than it (this map, one thread, build container: the reference 374 s, the port 253 s)"
-                   % (CPU_CROP, CPU_KP, CPU_OF, CPU_MATCH[0], CPU_MATCH[1], C2_K, C2_D, C2_M))
+def cpu_sample_text(preset="full"):
+    side, n_kp, n_of, n_hi = CPU_PRESETS[preset]
+    return ("stage-wise sample of the C2 map per process: build_space + find_anchors on an %d^3 occupancy-matched crop "
+            "(scaled per padded base voxel), assign_orientations on %d keypoints, generate_descriptors on %d oriented "
+            "features, the matching lines on a %d x %d block; scaled to the map's V1 = 274^3, K = %d, D = %d, M = %d; "
+            "oracle/mad_oracle.py = vectorised NumPy/SciPy port, bit-exact with the reference on the fixtures and 1.5x "
+            "faster than it (this map, one thread, build container: the reference 374 s, the port 253 s)"
+            % (side, n_kp, n_of, n_hi, CPU_MATCH[1], C2_K, C2_D, C2_M))
+
+
+CPU_SAMPLE_TEXT = cpu_sample_text("full")
 
 
 def host_procs():
@@ -173,12 +178,13 @@ def run_reference(args):
     preset = "full" if per_step >= 12.0 else ("half" if per_step >= 6.0 else "quarter")
     value, s_per_step, unit = cpu_stage_sample(grid, C2["voxelsp"], procs, args.steps, args.warmup, v1, preset=preset)
     unit["sample_preset"] = preset
+    sample_text = cpu_sample_text(preset)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": s_per_step * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32 grids, f64 line accumulation (SciPy)",
-        "data": "synthetic", "config": {"workload": workload_name(), "sample": CPU_SAMPLE_TEXT},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": CPU_SAMPLE_TEXT,
+        "data": "synthetic", "config": {"workload": workload_name(), "sample": sample_text},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": "port", "sample": sample_text,
                          "per_unit_seconds": unit},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
