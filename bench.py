@@ -486,7 +486,7 @@ def bench_c2(ctx, args):
         "e2e": {"value": ctx.world * n_vox / (ms_e2e / args.steps * 1e-3), "unit": UNIT,
                 "h2d_bytes_per_step": int(grid_pin.numel() * 4), "d2h_bytes_per_step": d2h, "d2h_detail": d2h_detail,
                 "d2h_format": "full (int16 descriptors, float64 scores)" if args.full_format else
-                              "compact (uint8 descriptors, int32 dot per pair + int32 squared norms; widened / scored on the host bit for bit)",
+                              "compact (uint8 descriptors; pairs as per-hi-row counts + lo index + int32 dot, + int32 squared norms; indices / scores rebuilt on the host bit for bit)",
                 "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches),
         "clocks": clocks,

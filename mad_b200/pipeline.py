@@ -499,6 +499,13 @@ def scores_from_dots(pair_hi, pair_lo, pair_dot, hi_norm2, lo_norm2):
     return out
 
 
+def pair_hi_from_counts(counts):
+    """Host side of the compact pair format: the hi index of every pair from the per-hi-row pair counts (the pair list is
+    in row-major order, so pair_hi is non-decreasing)."""
+    counts = np.asarray(counts)
+    return np.repeat(np.arange(len(counts), dtype=np.int32), counts)
+
+
 def match_threshold(hi, lo, cc=0.6, impl=None, want="score"):
     """Pairs (i, j) with cosine(hi_i, lo_j) > cc in row-major order (mad/MaD.py:420-424).
     Returns (hi index int32 [P], lo index int32 [P], score float64 [P]) as device tensors; want="dot" (uint8 kernel only)
@@ -658,9 +665,10 @@ class MapStream(object):
 
     def __init__(self, hi=None, cc=0.6, exact_f64=True, match_impl=None, patch_size=16, depth=2, download=True, compact=False):
         """compact=True: results travel in the compact wire format -- descriptors as the uint8 matching operand
-        (``dsc_u8``; entries are vote counts <= 255, widen with ``.astype(np.int16)``), pairs as (hi, lo, exact int32 dot)
-        + the map's squared norms (``pair_dot``, ``lo_norm2``; ``scores_from_dots`` gives the float64 scores bit for bit):
-        85 MB instead of 140 MB per C2 map over PCIe."""
+        (``dsc_u8``; entries are vote counts <= 255, widen with ``.astype(np.int16)``), pairs as per-hi-row counts + (lo,
+        exact int32 dot) + the map's squared norms (``pair_hi_counts``, ``pair_lo``, ``pair_dot``, ``lo_norm2``;
+        ``pair_hi_from_counts`` / ``scores_from_dots`` rebuild the indices and the float64 scores bit for bit):
+        70 MB instead of 140 MB per C2 map over PCIe."""
         _require_cuda()
         self.compact = bool(compact)
         self.download = download                        # False: results stay on the device (result() returns CUDA tensors)
@@ -717,7 +725,12 @@ class MapStream(object):
         if self.hi is not None:
             if self.compact:
                 ph, pl, dot = match_threshold(self.hi, lo, self.cc, impl=self.impl, want="dot")
-                out.update(pair_hi=get("ph", ph), pair_lo=get("pl", pl), pair_dot=get("pd", dot))
+                # the list is sorted by hi row: the per-row pair counts (4 B per hi row) carry pair_hi (4 B per PAIR) --
+                # ``pair_hi_from_counts`` expands them on the host
+                cnt = torch.zeros(self.hi.rows, dtype=torch.int32, device=ph.device)      # (no bincount: it synchronises)
+                if ph.numel():
+                    cnt.scatter_add_(0, ph.long(), torch.ones_like(ph))
+                out.update(pair_hi_counts=get("pc", cnt), pair_lo=get("pl", pl), pair_dot=get("pd", dot))
             else:
                 ph, pl, sc = match_threshold(self.hi, lo, self.cc, impl=self.impl)
                 out.update(pair_hi=get("ph", ph), pair_lo=get("pl", pl), score=get("sc", sc))

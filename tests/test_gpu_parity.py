@@ -482,8 +482,9 @@ def test_map_stream_compact_format(P):
         ph, pl, sc = P.match_threshold(hi, P.DescriptorSet(dsc), 0.6)
         out = ms.result(ms.submit(ms.upload(torch.from_numpy(g).pin_memory())))
         assert out["dsc_u8"].dtype == torch.uint8 and np.array_equal(out["dsc_u8"].numpy().astype(np.int16), dsc.cpu().numpy())
-        assert np.array_equal(out["pair_hi"].numpy(), ph.cpu().numpy()) and np.array_equal(out["pair_lo"].numpy(), pl.cpu().numpy())
-        got = P.scores_from_dots(out["pair_hi"].numpy(), out["pair_lo"].numpy(), out["pair_dot"].numpy(), hi.norm2.cpu().numpy(),
+        pair_hi = P.pair_hi_from_counts(out["pair_hi_counts"].numpy())
+        assert np.array_equal(pair_hi, ph.cpu().numpy()) and np.array_equal(out["pair_lo"].numpy(), pl.cpu().numpy())
+        got = P.scores_from_dots(pair_hi, out["pair_lo"].numpy(), out["pair_dot"].numpy(), hi.norm2.cpu().numpy(),
                                  out["lo_norm2"].numpy())
         assert np.array_equal(got, sc.cpu().numpy())
 
