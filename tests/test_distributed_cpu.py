@@ -80,7 +80,11 @@ def _worker(rank, world, port, q):
             mi2, ms2 = par.match_topk_grid(None, None, k, len(hi), grid, local=(torch.from_numpy(gi), torch.from_numpy(gs)))
             mi2, ms2 = mi2.numpy(), ms2.numpy()
             ok_grid = ok_grid and bool(np.array_equal(ms2, osc) and np.array_equal(mi2[ms2 > osc[:, -1:]], oi[osc > osc[:, -1:]]))
-        q.put((rank, ok_topk, ok_var, units, ok_thr, ok_grid))
+        # batch path: per-map tables of 5 maps (map u -> rank u mod G) collected on every rank, int16 rows of differing counts
+        tabs = [torch.full((u + 1, 4), u, dtype=torch.int16) for u in par.assign_units(5, rank, world)]
+        allt = par.collect_units(tabs, 5, like=torch.empty((0, 4), dtype=torch.int16))
+        ok_units = [tuple(t.shape) for t in allt] == [(u + 1, 4) for u in range(5)] and all(int(t[0, 0]) == u for u, t in enumerate(allt))
+        q.put((rank, ok_topk, ok_var, units, ok_thr, ok_grid, ok_units))
     finally:
         dist.destroy_process_group()
 
@@ -128,3 +132,4 @@ def test_world_size_2_gloo_topk_merge_and_varlen_gather():
     assert res[0][3] == [0, 2, 4, 6] and res[1][3] == [1, 3, 5]
     assert all(r[4] for r in res), "sharded threshold pair lists, gathered and merged, differ from the unsharded oracle"
     assert all(r[5] for r in res), "2-D rank grid top-k differs from the unsharded oracle"
+    assert all(r[6] for r in res), "collect_units returned wrong per-map tables"
