@@ -134,8 +134,9 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
     GaussStream<GR> gs;
     gs.init();
     for (int s = 0; s < n; s += C, b0 = (b0 == 32) ? 0 : b0 + 16) {
-        if (GR > 0 && s >= 48 && s + 50 < n) {
+        if (GR > 0 && s >= 16 && s + 50 < n) {
             // ---- interior chunk, fully unrolled: no boundary cases, constant pivot, static ring slots ----
+            // (from s = 16 on: the pivots equal their limit bit for bit from i = 15, checked in fill_spline_params)
             // invariant on entry: the forward sweep has reached fwd = s + 32 (ring holds x[s .. s+31])
             double* r0 = ring + b0 * rs;                                  // samples s    .. s+15
             double* r1 = ring + ((b0 >= 32) ? b0 - 32 : b0 + 16) * rs;    // samples s+16 .. s+31
@@ -336,12 +337,13 @@ spline_up_z_kernel(const float* __restrict__ in, double* __restrict__ out, int n
     spline_line<GR, 32>(io, n, prm, ring + lane);
 }
 
-static void fill_spline_params(SplineParams& p, const double* gw, int radius) {
+static bool fill_spline_params(SplineParams& p, const double* gw, int radius) {
     p.cprime[0] = p.cprime[1] = 0.0;
     p.cprime[2] = 0.25;
     for (int i = 3; i < 40; ++i) p.cprime[i] = 1.0 / (4.0 - p.cprime[i - 1]);
     for (int j = 0; j < 9; ++j) p.gw[j] = 0.0;
     for (int j = 0; j <= radius; ++j) p.gw[j] = gw ? gw[radius + j] : (j == 0 ? 1.0 : 0.0);
+    return p.cprime[15] == p.cprime[39];   // the unrolled chunks use the limit pivot for every row >= 16
 }
 
 extern "C" size_t mad_upsample_workspace_bytes(int bx, int by, int bz) {
@@ -397,7 +399,10 @@ extern "C" int mad_upsample_presmooth(const float* base, int bx, int by, int bz,
     MAD_CHECK_ARG(2 * bx - 1 > radius && 2 * by - 1 > radius && 2 * bz - 1 > radius);
     MAD_CHECK_ARG(workspace_bytes >= mad_upsample_workspace_bytes(bx, by, bz));
     SplineParams prm;
-    fill_spline_params(prm, gauss_w_host, radius);
+    if (!fill_spline_params(prm, gauss_w_host, radius)) {
+        mad_set_error("mad_upsample_presmooth: Thomas pivots have not converged by row 15 on this host");
+        return MAD_ERR_ARG;
+    }
     double* wsA = reinterpret_cast<double*>(workspace);
     double* wsB = reinterpret_cast<double*>(reinterpret_cast<char*>(workspace) +
                                             mad_align_up((size_t)bx * by * (2 * (size_t)bz - 1) * sizeof(double), 256));
