@@ -6,6 +6,7 @@
 // All kernels are HBM-bound stencils: marching kernels with register windows for the strided
 // axes (coalesced across the contiguous z index), shared-memory row staging for the z axis.
 #include <stdlib.h>
+#include <type_traits>
 
 #include "common.cuh"
 
@@ -134,40 +135,67 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
     GaussStream<GR> gs;
     gs.init();
     for (int s = 0; s < n; s += C, b0 = (b0 == 32) ? 0 : b0 + 16) {
-        if (GR > 0 && s >= 16 && s + 50 < n) {
-            // ---- interior chunk, fully unrolled: no boundary cases, constant pivot, static ring slots ----
+        if (GR > 0 && s >= 16 && s + 19 <= n) {
+            // ---- unrolled chunk: constant pivot, static ring slots ----
             // (from s = 16 on: the pivots equal their limit bit for bit from i = 15, checked in fill_spline_params)
-            // invariant on entry: the forward sweep has reached fwd = s + 32 (ring holds x[s .. s+31])
+            // invariant on entry: the forward sweep has reached fwd = min(s + 32, last + 1) (ring holds x[s .. fwd-1]).
+            // interior (s + 50 < n): no boundary case at all.  TAIL (the last rows are within the look-ahead): forward
+            // and backward steps beyond row `last` are predicated off, the last row takes its not-a-knot term; the
+            // chunk's own 16 samples and sample s + 16 are all <= last, so the output phase is the interior's.
             double* r0 = ring + b0 * rs;                                  // samples s    .. s+15
             double* r1 = ring + ((b0 >= 32) ? b0 - 32 : b0 + 16) * rs;    // samples s+16 .. s+31
             double* r2 = ring + ((b0 >= 16) ? b0 - 16 : b0 + 32) * rs;    // samples s+32 .. s+47
-            {
-                double yy[16];
+            double Me;
+            auto sweeps = [&](auto tail_c) {
+                constexpr bool TAIL = decltype(tail_c)::value;
+                const int nf = last - (s + 32) + 1;                        // forward steps left (TAIL: may be < 16, even <= 0)
+                {
+                    double yy[16];
 #pragma unroll
-                for (int q = 0; q < 16; ++q) yy[q] = io.y(s + 33 + q);
+                    for (int q = 0; q < 16; ++q) yy[q] = (!TAIL || q < nf) ? io.y(s + 33 + q) : 0.0;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) {
-                    const double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
-                    const double x = (r - xprev) * cinf;
-                    r2[q * rs] = x;
-                    xprev = x;
-                    ya = yb;
-                    yb = yy[q];
+                    for (int q = 0; q < 16; ++q) {
+                        if (!TAIL || q < nf) {
+                            double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
+                            if (TAIL && q == nf - 1) r -= Mn2;
+                            const double x = (r - xprev) * cinf;
+                            r2[q * rs] = x;
+                            xprev = x;
+                            ya = yb;
+                            yb = yy[q];
+                        }
+                    }
+                    fwd += TAIL ? max(0, min(16, nf)) : 16;
                 }
-                fwd += 16;
-            }
-            double M = r2[15 * rs];
+                // rows above `last` do not exist: starting from M = 0, the first existing row gives M = x[last] exactly
+                const int nb = last - s;                                   // highest existing offset in the 48-row window
+                double M = TAIL ? 0.0 : r2[15 * rs];
 #pragma unroll
-            for (int d = 14; d >= 0; --d) M = fma(-cinf, M, r2[d * rs]);
+                for (int d = 15; d >= 0; --d) {
+                    if (!TAIL && d == 15) continue;
+                    if (!TAIL || 32 + d <= nb) {
+                        M = fma(-cinf, M, r2[d * rs]);
+                        if (TAIL && 32 + d == nb) Mn3v = M;
+                    }
+                }
 #pragma unroll
-            for (int d = 15; d >= 1; --d) M = fma(-cinf, M, r1[d * rs]);
-            const double Me = fma(-cinf, M, r1[0]);                       // M[s+16]
-            M = Me;
+                for (int d = 15; d >= 1; --d) {
+                    if (!TAIL || 16 + d <= nb) {
+                        M = fma(-cinf, M, r1[d * rs]);
+                        if (TAIL && 16 + d == nb) Mn3v = M;
+                    }
+                }
+                Me = fma(-cinf, M, r1[0]);                                // M[s+16]
+                if (TAIL && nb == 16) Mn3v = Me;
+                M = Me;
 #pragma unroll
-            for (int d = 15; d >= 0; --d) {
-                M = fma(-cinf, M, r0[d * rs]);
-                r0[d * rs] = M;
-            }
+                for (int d = 15; d >= 0; --d) {
+                    M = fma(-cinf, M, r0[d * rs]);
+                    r0[d * rs] = M;
+                }
+            };
+            if (s + 50 < n) sweeps(std::false_type{});
+            else sweeps(std::true_type{});
             double yn[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) yn[q] = io.y(s + 1 + q);
