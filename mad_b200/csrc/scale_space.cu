@@ -59,6 +59,7 @@ extern "C" int mad_pad3d(const float* in, int nx, int ny, int nz, int pad, float
 struct SplineParams {
     double cprime[40];  // Thomas pivots c'_i = 1/(4 - c'_{i-1}), c'_2 = 1/4 (constant beyond ~i=25)
     double gw[9];       // presmoothing weights gw[|j|], j = 0..GR
+    int long_min;       // lines of at least this many samples take spline_line_long (>= 64; env MAD_SPLINE_GENERIC: never)
 };
 
 template <int GR>
@@ -97,6 +98,19 @@ struct GaussStream {
             emit(io, gw);
         }
     }
+    // p-th push of the line with p known at compile time (unrolled head chunk): the fill / mirror / emit cases fold away
+    template <class IO>
+    __device__ __forceinline__ void push_at(int p, double v, IO& io, const double* gw) {
+#pragma unroll
+        for (int i = 0; i < 2 * GR; ++i) w[i] = w[i + 1];
+        w[2 * GR] = v;
+        ++cnt;
+        if (p == GR) {
+#pragma unroll
+            for (int t = 0; t < GR; ++t) w[GR - 1 - t] = w[GR + t];
+        }
+        if (p >= GR) emit(io, gw);
+    }
     // interior of the line: the window is full, every push emits
     template <class IO>
     __device__ __forceinline__ void push_steady(double v, IO& io, const double* gw) {
@@ -118,11 +132,205 @@ struct GaussStream {
 // ring slot of sample i: i mod 48 (48 = chunk + look-ahead; exact for i < 130 000)
 __device__ __forceinline__ int ring_slot(int i) { return i - 48 * ((i * 43691) >> 21); }
 
+// Lines of n >= 64 samples (every real map: the padded grids are >= 100 long).  Same arithmetic, in the same order, as
+// spline_line below; what differs is the control flow, which is straight-line everywhere but in the last <= 18 samples:
+//   head     forward rows 2..31 in two batches of 15 loads, then chunk 0 with the varying pivots as immediates and the
+//            Gaussian window's fill / mirror cases folded at compile time;
+//   interior chunks of 16 samples while the 32-row look-ahead stays below the last row (s + 50 < n);
+//   final    ONE sweep whose look-ahead reaches the last row: the back substitution starts at the true last row, so it
+//            yields M for every remaining row (35..50 of them); they are parked in the ring and the remaining samples
+//            are emitted without further sweeps: two unrolled blocks of 16, then a compact loop for the last 3..18.
+template <int GR, int RS, class IO>
+__device__ __forceinline__ void spline_line_long(IO& io, const int n, const SplineParams& prm, double* ring) {
+    constexpr int rs = RS;
+    const double cinf = prm.cprime[39];
+    const int last = n - 3;
+    const double M1 = (io.y(0) - 2.0 * io.y(1)) + io.y(2);
+    const double Mn2 = (io.y(n - 3) - 2.0 * io.y(n - 2)) + io.y(n - 1);
+    double xprev = 0.0;
+    double ya = io.y(1), yb = io.y(2);
+    GaussStream<GR> gs;
+    gs.init();
+
+    // forward rows f0 .. f0+15 into seg[0..15] with the limit pivot
+    auto forward16 = [&](int f0, double* seg) {
+        double yy[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) yy[q] = io.y(f0 + 1 + q);
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
+            const double x = (r - xprev) * cinf;
+            seg[q * rs] = x;
+            xprev = x;
+            ya = yb;
+            yb = yy[q];
+        }
+    };
+    // samples s0 .. s0+15 and the half steps after them; seg holds M[s0 .. s0+15], Mnext = M[s0+16]
+    auto emit16 = [&](int s0, const double* seg, double M0, double Mnext, auto head_c) {
+        constexpr bool HEAD = decltype(head_c)::value;
+        double yn[16];
+#pragma unroll
+        for (int q = 0; q < 16; ++q) yn[q] = io.y(s0 + 1 + q);
+        double yi = io.y(s0);
+        double Mi = M0;
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            double Mn = (q < 15) ? seg[(q < 15 ? q + 1 : 0) * rs] : Mnext;
+            if (HEAD && q == 0) Mn = M1;                                  // M[1]
+            const double h = 0.5 * (yi + yn[q]) - (Mi + Mn) * 0.0625;
+            if (HEAD) {
+                gs.push_at(2 * q, yi, io, prm.gw);
+                gs.push_at(2 * q + 1, h, io, prm.gw);
+            } else {
+                gs.push_steady(yi, io, prm.gw);
+                gs.push_steady(h, io, prm.gw);
+            }
+            Mi = Mn;
+            yi = yn[q];
+        }
+        io.chunk_done();
+    };
+
+    // ---- head: rows 2..31 forward (pivots still converging: immediates), then chunk 0 ----
+    {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            double yy[15];
+#pragma unroll
+            for (int q = 0; q < 15; ++q) yy[q] = io.y(3 + 15 * h + q);
+#pragma unroll
+            for (int q = 0; q < 15; ++q) {
+                const int f = 2 + 15 * h + q;
+                double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
+                if (f == 2) r -= M1;
+                const double x = (r - xprev) * prm.cprime[f];
+                ring[f * rs] = x;
+                xprev = x;
+                ya = yb;
+                yb = yy[q];
+            }
+        }
+        double* r0 = ring;
+        double* r1 = ring + 16 * rs;
+        double* r2 = ring + 32 * rs;
+        forward16(32, r2);
+        double M = r2[15 * rs];
+#pragma unroll
+        for (int d = 14; d >= 0; --d) M = fma(-cinf, M, r2[d * rs]);
+#pragma unroll
+        for (int d = 15; d >= 1; --d) M = fma(-cinf, M, r1[d * rs]);
+        const double Me = fma(-cinf, M, r1[0]);
+        M = Me;
+#pragma unroll
+        for (int d = 15; d >= 2; --d) {
+            M = fma(-prm.cprime[d], M, r0[d * rs]);
+            r0[d * rs] = M;
+        }
+        r0[rs] = M1;                                                      // M[1]; M now holds M[2]
+        emit16(0, r0, 2.0 * M1 - M, Me, std::true_type{});
+    }
+
+    // ---- interior chunks ----
+    int s = 16, b0 = 16;
+    for (; s + 50 < n; s += 16, b0 = (b0 == 32) ? 0 : b0 + 16) {
+        double* r0 = ring + b0 * rs;                                  // samples s    .. s+15
+        double* r1 = ring + ((b0 >= 32) ? b0 - 32 : b0 + 16) * rs;    // samples s+16 .. s+31
+        double* r2 = ring + ((b0 >= 16) ? b0 - 16 : b0 + 32) * rs;    // samples s+32 .. s+47
+        forward16(s + 32, r2);
+        double M = r2[15 * rs];
+#pragma unroll
+        for (int d = 14; d >= 0; --d) M = fma(-cinf, M, r2[d * rs]);
+#pragma unroll
+        for (int d = 15; d >= 1; --d) M = fma(-cinf, M, r1[d * rs]);
+        const double Me = fma(-cinf, M, r1[0]);                       // M[s+16]
+        M = Me;
+#pragma unroll
+        for (int d = 15; d >= 0; --d) {
+            M = fma(-cinf, M, r0[d * rs]);
+            r0[d * rs] = M;
+        }
+        emit16(s, r0, r0[0], Me, std::false_type{});
+    }
+
+    // ---- final sweep at s (n - 50 <= s <= n - 35): rows s+32 .. last forward, then M for all rows last .. s ----
+    {
+        double* r0 = ring + b0 * rs;
+        double* r1 = ring + ((b0 >= 32) ? b0 - 32 : b0 + 16) * rs;
+        double* r2 = ring + ((b0 >= 16) ? b0 - 16 : b0 + 32) * rs;
+        const int nf = last - (s + 32) + 1;                           // 1 .. 16 forward rows are left
+        {
+            double yy[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) yy[q] = (q < nf) ? io.y(s + 33 + q) : 0.0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                if (q < nf) {
+                    double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
+                    if (q == nf - 1) r -= Mn2;                        // the last row's not-a-knot term
+                    const double x = (r - xprev) * cinf;
+                    r2[q * rs] = x;
+                    xprev = x;
+                    ya = yb;
+                    yb = yy[q];
+                }
+            }
+        }
+        // rows above `last` do not exist: from M = 0 the first existing row gives M = x[last] exactly
+        double M = 0.0;
+#pragma unroll
+        for (int d = 15; d >= 0; --d) {
+            if (d < nf) {
+                M = fma(-cinf, M, r2[d * rs]);
+                r2[d * rs] = M;
+            }
+        }
+#pragma unroll
+        for (int d = 15; d >= 0; --d) {
+            M = fma(-cinf, M, r1[d * rs]);
+            r1[d * rs] = M;
+        }
+#pragma unroll
+        for (int d = 15; d >= 0; --d) {
+            M = fma(-cinf, M, r0[d * rs]);
+            r0[d * rs] = M;
+        }
+        const double Mlast = r2[(nf - 1) * rs];                       // M[n-3]
+        emit16(s, r0, r0[0], r1[0], std::false_type{});
+        emit16(s + 16, r1, r1[0], r2[0], std::false_type{});
+        // ---- the last 3 .. 18 samples: rows s+32 .. n-1 (M of rows <= last in r2, the two end rows from the not-a-knot rule) ----
+        int i = s + 32;
+        double yi = io.y(i);
+        double Mi = r2[0];
+#pragma unroll 1
+        for (; i < n; ++i) {
+            gs.push_steady(yi, io, prm.gw);
+            if (i + 1 < n) {
+                const int i1 = i + 1;
+                const int d1 = min(i1 - (s + 32), 15);                // in-range ring row also where the value is not used
+                const double Mr = r2[d1 * rs];
+                const double Mn = (i1 == n - 2) ? Mn2 : (i1 == n - 1) ? 2.0 * Mn2 - Mlast : Mr;
+                const double yn = io.y(i1);
+                gs.push_steady(0.5 * (yi + yn) - (Mi + Mn) * 0.0625, io, prm.gw);
+                Mi = Mn;
+                yi = yn;
+            }
+        }
+    }
+    gs.finish(io, prm.gw);
+    io.chunk_done();
+}
+
 template <int GR, int RS, class IO>
 __device__ __forceinline__ void spline_line(IO& io, const int n, const SplineParams& prm, double* ring) {
+    if (GR > 0 && n >= prm.long_min) {
+        spline_line_long<GR, RS>(io, n, prm, ring);
+        return;
+    }
+    // short lines (and the radius-0 filter): one generic chunk loop with every boundary case in it
     constexpr int C = 16, L = 32;
-    constexpr int rs = RS;                         // ring stride in doubles: compile-time, so that the fully
-                                                   // unrolled interior chunk addresses the ring with immediates
+    constexpr int rs = RS;                         // ring stride in doubles
     const double cinf = prm.cprime[39];            // the pivots have converged to 2 - sqrt(3) long before i = 39
     int b0 = 0;                                    // ring slot of sample s (s is a multiple of 16: 0, 16, 32, 0, ...)
     const int last = n - 3;
@@ -135,83 +343,6 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
     GaussStream<GR> gs;
     gs.init();
     for (int s = 0; s < n; s += C, b0 = (b0 == 32) ? 0 : b0 + 16) {
-        if (GR > 0 && s >= 16 && s + 19 <= n) {
-            // ---- unrolled chunk: constant pivot, static ring slots ----
-            // (from s = 16 on: the pivots equal their limit bit for bit from i = 15, checked in fill_spline_params)
-            // invariant on entry: the forward sweep has reached fwd = min(s + 32, last + 1) (ring holds x[s .. fwd-1]).
-            // interior (s + 50 < n): no boundary case at all.  TAIL (the last rows are within the look-ahead): forward
-            // and backward steps beyond row `last` are predicated off, the last row takes its not-a-knot term; the
-            // chunk's own 16 samples and sample s + 16 are all <= last, so the output phase is the interior's.
-            double* r0 = ring + b0 * rs;                                  // samples s    .. s+15
-            double* r1 = ring + ((b0 >= 32) ? b0 - 32 : b0 + 16) * rs;    // samples s+16 .. s+31
-            double* r2 = ring + ((b0 >= 16) ? b0 - 16 : b0 + 32) * rs;    // samples s+32 .. s+47
-            double Me;
-            auto sweeps = [&](auto tail_c) {
-                constexpr bool TAIL = decltype(tail_c)::value;
-                const int nf = last - (s + 32) + 1;                        // forward steps left (TAIL: may be < 16, even <= 0)
-                {
-                    double yy[16];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) yy[q] = (!TAIL || q < nf) ? io.y(s + 33 + q) : 0.0;
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        if (!TAIL || q < nf) {
-                            double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
-                            if (TAIL && q == nf - 1) r -= Mn2;
-                            const double x = (r - xprev) * cinf;
-                            r2[q * rs] = x;
-                            xprev = x;
-                            ya = yb;
-                            yb = yy[q];
-                        }
-                    }
-                    fwd += TAIL ? max(0, min(16, nf)) : 16;
-                }
-                // rows above `last` do not exist: starting from M = 0, the first existing row gives M = x[last] exactly
-                const int nb = last - s;                                   // highest existing offset in the 48-row window
-                double M = TAIL ? 0.0 : r2[15 * rs];
-#pragma unroll
-                for (int d = 15; d >= 0; --d) {
-                    if (!TAIL && d == 15) continue;
-                    if (!TAIL || 32 + d <= nb) {
-                        M = fma(-cinf, M, r2[d * rs]);
-                        if (TAIL && 32 + d == nb) Mn3v = M;
-                    }
-                }
-#pragma unroll
-                for (int d = 15; d >= 1; --d) {
-                    if (!TAIL || 16 + d <= nb) {
-                        M = fma(-cinf, M, r1[d * rs]);
-                        if (TAIL && 16 + d == nb) Mn3v = M;
-                    }
-                }
-                Me = fma(-cinf, M, r1[0]);                                // M[s+16]
-                if (TAIL && nb == 16) Mn3v = Me;
-                M = Me;
-#pragma unroll
-                for (int d = 15; d >= 0; --d) {
-                    M = fma(-cinf, M, r0[d * rs]);
-                    r0[d * rs] = M;
-                }
-            };
-            if (s + 50 < n) sweeps(std::false_type{});
-            else sweeps(std::true_type{});
-            double yn[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) yn[q] = io.y(s + 1 + q);
-            double yi = io.y(s);
-            double Mi = r0[0];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const double Mn = (q < 15) ? r0[(q < 15 ? q + 1 : 0) * rs] : Me;
-                gs.push_steady(yi, io, prm.gw);
-                gs.push_steady(0.5 * (yi + yn[q]) - (Mi + Mn) * 0.0625, io, prm.gw);
-                Mi = Mn;
-                yi = yn[q];
-            }
-            io.chunk_done();
-            continue;
-        }
         const int e = min(s + C, n);
         const int top = min(e + L - 1, last);
         while (fwd <= top) {  // forward Thomas sweep, loads batched 8 deep to keep HBM requests in flight
@@ -371,7 +502,8 @@ static bool fill_spline_params(SplineParams& p, const double* gw, int radius) {
     for (int i = 3; i < 40; ++i) p.cprime[i] = 1.0 / (4.0 - p.cprime[i - 1]);
     for (int j = 0; j < 9; ++j) p.gw[j] = 0.0;
     for (int j = 0; j <= radius; ++j) p.gw[j] = gw ? gw[radius + j] : (j == 0 ? 1.0 : 0.0);
-    return p.cprime[15] == p.cprime[39];   // the unrolled chunks use the limit pivot for every row >= 16
+    p.long_min = getenv("MAD_SPLINE_GENERIC") ? 0x7fffffff : 64;
+    return p.cprime[15] == p.cprime[39];   // the unrolled chunks use the limit pivot for every row >= 15
 }
 
 extern "C" size_t mad_upsample_workspace_bytes(int bx, int by, int bz) {

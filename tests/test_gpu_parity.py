@@ -141,6 +141,29 @@ def test_stages_against_oracle_inputs(P):
     assert np.array_equal(dsc.cpu().numpy(), odsc)
 
 
+@pytest.mark.parametrize("shape", [(64, 70, 76), (65, 71, 77), (66, 72, 78), (67, 73, 79), (68, 74, 80), (69, 75, 81)])
+def test_spline_line_lengths(P, shape):
+    """a2 on lines of every length class (n mod 16 = 0..15, both sides of the look-ahead boundaries): the long-line
+    control flow of the spline kernels (head / interior chunks / one final sweep / compact tail) gives the very bits of
+    the generic chunk loop, and both equal the oracle's interp1d + gaussian_filter (mad/MapSpace.py:137-146)."""
+    import os
+    import mad_oracle as mo
+    from scipy import ndimage as ndi
+    rng = np.random.default_rng(sum(shape))
+    g = ndi.gaussian_filter(rng.random(shape), 1.5).astype(np.float32)
+    g[rng.random(shape) < 0.3] = 0.0                                   # maps are zero over most of the box
+    fast = P.build_space(g, map_padding=0, oct_mode="up", full_gradient=False).grids[0].clone()
+    os.environ["MAD_SPLINE_GENERIC"] = "1"
+    try:
+        slow = P.build_space(g, map_padding=0, oct_mode="up", full_gradient=False).grids[0].clone()
+    finally:
+        del os.environ["MAD_SPLINE_GENERIC"]
+    assert torch.equal(fast, slow)
+    want = ndi.gaussian_filter(mo.upsample2(g), sigma=1).astype(np.float32)
+    assert tuple(fast.shape) == want.shape
+    assert H.equal_flushed(fast.cpu().numpy(), want)
+
+
 @pytest.mark.parametrize("shape", [(20, 22, 24), (31, 17, 23)])
 def test_ragged_and_empty_maps(P, shape):
     """Non-cubic maps and an all-zero map (no keypoints, no descriptors) -- reference edge cases."""
