@@ -155,8 +155,7 @@ __device__ __forceinline__ void spline_line_long(IO& io, const int n, const Spli
     // forward rows f0 .. f0+15 into seg[0..15] with the limit pivot
     auto forward16 = [&](int f0, double* seg) {
         double yy[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) yy[q] = io.y(f0 + 1 + q);
+        io.load_run(f0 + 1, yy);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             const double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
@@ -170,16 +169,15 @@ __device__ __forceinline__ void spline_line_long(IO& io, const int n, const Spli
     // samples s0 .. s0+15 and the half steps after them; seg holds M[s0 .. s0+15], Mnext = M[s0+16]
     auto emit16 = [&](int s0, const double* seg, double M0, double Mnext, auto head_c) {
         constexpr bool HEAD = decltype(head_c)::value;
-        double yn[16];
-#pragma unroll
-        for (int q = 0; q < 16; ++q) yn[q] = io.y(s0 + 1 + q);
-        double yi = io.y(s0);
+        double yn[17];                                                    // y[s0 .. s0+16]
+        io.load_run(s0, yn);
+        double yi = yn[0];
         double Mi = M0;
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
             double Mn = (q < 15) ? seg[(q < 15 ? q + 1 : 0) * rs] : Mnext;
             if (HEAD && q == 0) Mn = M1;                                  // M[1]
-            const double h = 0.5 * (yi + yn[q]) - (Mi + Mn) * 0.0625;
+            const double h = 0.5 * (yi + yn[q + 1]) - (Mi + Mn) * 0.0625;
             if (HEAD) {
                 gs.push_at(2 * q, yi, io, prm.gw);
                 gs.push_at(2 * q + 1, h, io, prm.gw);
@@ -188,7 +186,7 @@ __device__ __forceinline__ void spline_line_long(IO& io, const int n, const Spli
                 gs.push_steady(h, io, prm.gw);
             }
             Mi = Mn;
-            yi = yn[q];
+            yi = yn[q + 1];
         }
         io.chunk_done();
     };
@@ -198,8 +196,7 @@ __device__ __forceinline__ void spline_line_long(IO& io, const int n, const Spli
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
             double yy[15];
-#pragma unroll
-            for (int q = 0; q < 15; ++q) yy[q] = io.y(3 + 15 * h + q);
+            io.load_run(3 + 15 * h, yy);
 #pragma unroll
             for (int q = 0; q < 15; ++q) {
                 const int f = 2 + 15 * h + q;
@@ -420,10 +417,23 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
 template <typename TIn, typename TOut>
 struct StridedIO {
     const TIn* yin;
-    TOut* uout;
-    long long stride;
+    TOut* uout;          // next output (the outputs of a line are written strictly in order)
+    int stride;          // elements between consecutive samples of the line (< 2^31: one IMAD.WIDE per address)
     __device__ __forceinline__ double y(int i) const { return (double)__ldg(yin + (long long)i * stride); }
-    __device__ __forceinline__ void put(int k, double v) { uout[(long long)k * stride] = (TOut)v; }
+    // samples i0 .. i0+CNT-1: one 64-bit multiply for the run, then a running pointer
+    template <int CNT>
+    __device__ __forceinline__ void load_run(int i0, double (&v)[CNT]) const {
+        const TIn* p = yin + (long long)i0 * stride;
+#pragma unroll
+        for (int q = 0; q < CNT; ++q) {
+            v[q] = (double)__ldg(p);
+            p += stride;
+        }
+    }
+    __device__ __forceinline__ void put(int, double v) {
+        *uout = (TOut)v;
+        uout += stride;
+    }
     __device__ __forceinline__ void chunk_done() {}
 };
 
@@ -438,7 +448,7 @@ spline_up_strided_kernel(const TIn* __restrict__ in, TOut* __restrict__ out, int
     StridedIO<TIn, TOut> io;
     io.yin = in + o * (long long)n * inner + j;
     io.uout = out + o * (long long)(2 * n - 1) * inner + j;
-    io.stride = inner;
+    io.stride = (int)inner;
     spline_line<GR, 128>(io, n, prm, ring_s + threadIdx.x);
 }
 
@@ -454,6 +464,11 @@ struct ZLineIO {
     int lane;
     int kbase, cnt;
     __device__ __forceinline__ double y(int i) const { return (double)__ldg(yline + i); }
+    template <int CNT>
+    __device__ __forceinline__ void load_run(int i0, double (&v)[CNT]) const {
+#pragma unroll
+        for (int q = 0; q < CNT; ++q) v[q] = (double)__ldg(yline + i0 + q);
+    }
     __device__ __forceinline__ void put(int k, double v) {
         ostage[lane * kZStage + (k - kbase)] = v;
         ++cnt;
@@ -558,6 +573,7 @@ extern "C" int mad_upsample_presmooth(const float* base, int bx, int by, int bz,
     MAD_CHECK_ARG(radius >= 0 && radius <= 8 && (radius == 0 || gauss_w_host));
     MAD_CHECK_ARG(2 * bx - 1 > radius && 2 * by - 1 > radius && 2 * bz - 1 > radius);
     MAD_CHECK_ARG(workspace_bytes >= mad_upsample_workspace_bytes(bx, by, bz));
+    MAD_CHECK_ARG((long long)by * (2 * (long long)bz - 1) < 0x7fffffffLL);      // line strides are 32-bit element counts
     SplineParams prm;
     if (!fill_spline_params(prm, gauss_w_host, radius)) {
         mad_set_error("mad_upsample_presmooth: Thomas pivots have not converged by row 15 on this host");
