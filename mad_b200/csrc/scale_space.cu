@@ -13,29 +13,32 @@
 // ------------------------------------------------------------------------------------------
 // a1: zero padding
 // ------------------------------------------------------------------------------------------
-__global__ void pad3d_kernel(const float* __restrict__ in, int nx, int ny, int nz, int pad,
-                             float* __restrict__ out, long long total) {
-    const int oy = ny + 2 * pad, oz = nz + 2 * pad;
-    for (long long g = blockIdx.x * (long long)blockDim.x + threadIdx.x; g < total;
-         g += (long long)gridDim.x * blockDim.x) {
-        int z = (int)(g % oz);
-        long long t = g / oz;
-        int y = (int)(t % oy);
-        int x = (int)(t / oy);
-        int sx = x - pad, sy = y - pad, sz = z - pad;
-        float v = 0.f;
-        if (sx >= 0 && sx < nx && sy >= 0 && sy < ny && sz >= 0 && sz < nz)
-            v = __ldg(in + ((long long)sx * ny + sy) * nz + sz);
-        out[g] = v;
+// One warp per output row (x, y): no per-element division, lanes sweep z (coalesced stores; the source row, when the row
+// is not padding, is read with the same lanes shifted by `pad`).
+__global__ void __launch_bounds__(256)
+pad3d_kernel(const float* __restrict__ in, int nx, int ny, int nz, int pad, float* __restrict__ out, int ox, int oy, int oz) {
+    const int lane = threadIdx.x & 31;
+    const long long rows = (long long)ox * oy;
+    for (long long row = (long long)blockIdx.x * 8 + (threadIdx.x >> 5); row < rows; row += (long long)gridDim.x * 8) {
+        const int x = (int)(row / oy), y = (int)(row - (long long)x * oy);
+        const int sx = x - pad, sy = y - pad;
+        float* o = out + row * oz;
+        if (sx < 0 || sx >= nx || sy < 0 || sy >= ny) {
+            for (int z = lane; z < oz; z += 32) o[z] = 0.f;
+        } else {
+            const float* src = in + ((long long)sx * ny + sy) * nz - pad;
+            for (int z = lane; z < oz; z += 32) o[z] = (z >= pad && z < nz + pad) ? __ldg(src + z) : 0.f;
+        }
     }
 }
 
 extern "C" int mad_pad3d(const float* in, int nx, int ny, int nz, int pad, float* out, void* stream) {
     MAD_CHECK_ARG(in && out && nx > 0 && ny > 0 && nz > 0 && pad >= 0);
-    long long total = (long long)(nx + 2 * pad) * (ny + 2 * pad) * (nz + 2 * pad);
-    int blocks = (int)std::min<long long>(mad_ceil_div(total, 256), (long long)mad_sm_count() * 16);
+    const int ox = nx + 2 * pad, oy = ny + 2 * pad, oz = nz + 2 * pad;
+    const long long rows = (long long)ox * oy;
+    int blocks = (int)std::min<long long>(mad_ceil_div(rows, 8), (long long)mad_sm_count() * 32);
     MAD_PROF("pad3d_kernel", stream);
-    pad3d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, nx, ny, nz, pad, out, total);
+    pad3d_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(in, nx, ny, nz, pad, out, ox, oy, oz);
     MAD_LAUNCH_OK();
     return MAD_OK;
 }
