@@ -161,8 +161,7 @@ __device__ __forceinline__ void spline_line_long(IO& io, const int n, const Spli
         io.load_run(f0 + 1, yy);
 #pragma unroll
         for (int q = 0; q < 16; ++q) {
-            const double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
-            const double x = (r - xprev) * cinf;
+            const double x = fma(6.0, (ya - 2.0 * yb) + yy[q], -xprev) * cinf;    // forward row: ONE rounding of 6 d - x', on every path
             seg[q * rs] = x;
             xprev = x;
             ya = yb;
@@ -203,9 +202,8 @@ __device__ __forceinline__ void spline_line_long(IO& io, const int n, const Spli
 #pragma unroll
             for (int q = 0; q < 15; ++q) {
                 const int f = 2 + 15 * h + q;
-                double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
-                if (f == 2) r -= M1;
-                const double x = (r - xprev) * prm.cprime[f];
+                const double a = (f == 2) ? M1 : xprev;                  // row 2: x' = 0, the not-a-knot term takes its place
+                const double x = fma(6.0, (ya - 2.0 * yb) + yy[q], -a) * prm.cprime[f];
                 ring[f * rs] = x;
                 xprev = x;
                 ya = yb;
@@ -267,9 +265,8 @@ __device__ __forceinline__ void spline_line_long(IO& io, const int n, const Spli
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
                 if (q < nf) {
-                    double r = 6.0 * ((ya - 2.0 * yb) + yy[q]);
-                    if (q == nf - 1) r -= Mn2;                        // the last row's not-a-knot term
-                    const double x = (r - xprev) * cinf;
+                    const double a = (q == nf - 1) ? xprev + Mn2 : xprev;   // the last row's not-a-knot term
+                    const double x = fma(6.0, (ya - 2.0 * yb) + yy[q], -a) * cinf;
                     r2[q * rs] = x;
                     xprev = x;
                     ya = yb;
@@ -354,10 +351,9 @@ __device__ __forceinline__ void spline_line(IO& io, const int n, const SplinePar
             for (int q = 0; q < 8; ++q) {
                 if (q < nb) {
                     const double yc = yy[q];
-                    double r = 6.0 * ((ya - 2.0 * yb) + yc);
-                    if (fwd == 2) r -= M1;
-                    if (fwd == last) r -= Mn2;
-                    const double x = (r - xprev) * prm.cprime[fwd < 39 ? fwd : 39];
+                    double a = (fwd == 2) ? M1 : xprev;                  // the same roundings as spline_line_long, row by row:
+                    if (fwd == last) a += Mn2;                           // boundary terms join x', then ONE fma per row
+                    const double x = fma(6.0, (ya - 2.0 * yb) + yc, -a) * prm.cprime[fwd < 39 ? fwd : 39];
                     ring[ring_slot(fwd) * rs] = x;
                     xprev = x;
                     ya = yb;
