@@ -2,68 +2,65 @@
 
 In this implementation the features live in device tables (pipeline.Keypoints / Oriented / the
 descriptor matrix); DensityFeature objects are the host-side view the reference's downstream
-Python (matching bookkeeping, clustering, refinement, HDF5 cache) consumes.
+Python (matching bookkeeping, clustering, refinement, HDF5 cache) consumes.  The attribute and
+setter names are the interface (``MaD._match_dsc`` and the cache read them, mad/MaD.py:416-451,
+849-852); the scratch arrays the reference parks on every feature (gradient patches, per-step
+histograms, VMD helpers) have no counterpart here -- those intermediates never leave the GPU.
 """
-import numpy as np
+
+# attribute -> value of a fresh record (the reference's defaults, mad/DensityFeature.py:6-33); `list` = a new empty list
+_FRESH = {
+    # detector level
+    "voxel_val": 0, "oct_scale": -1, "coords": list, "map_coords": list, "subv_map_coords": list, "ratio": 0,
+    # orientation level
+    "eqsp_size": -1, "main_bin": -1, "sec_bin": -1, "list_bins": list, "list_sec_bins": list,
+    "to_dom_mat": list, "adj_sec_mat": list, "Rfinal": list,
+    # descriptor level
+    "lin_ar_subeqsp": list,
+}
 
 
 class DensityFeature(object):
     def __init__(self):
-        # detector level
-        self.voxel_val = 0
-        self.oct_scale = -1
-        self.coords = []
-        self.map_coords = []
-        self.subv_map_coords = []
-        self.ratio = 0
-        # orientation level
-        self.eqsp_size = -1
-        self.main_bin = -1
-        self.sec_bin = -1
-        self.list_bins = []
-        self.list_sec_bins = []
-        self.to_dom_mat = []
-        self.adj_sec_mat = []
-        self.Rfinal = []
-        # descriptor level
-        self.lin_ar_subeqsp = []
+        for name, fresh in _FRESH.items():
+            setattr(self, name, fresh() if fresh is list else fresh)
+
+    def _take(self, **fields):
+        self.__dict__.update(fields)
+
+    def _patch_geometry(self, radius):
+        self._take(box_size=2 * radius + 1, box_side=radius)
 
     def set_detector_info(self, index, oct_scale, coords, map_coords, subv_map_coords, voxel_val):
-        self.index = index
-        self.oct_scale = oct_scale
-        self.coords = coords
-        self.map_coords = map_coords
-        self.subv_map_coords = subv_map_coords
-        self.voxel_val = voxel_val
+        """mad/DensityFeature.py:35-41 (called by Detector.find_anchors, mad/Detector.py:126-128)."""
+        self._take(index=index, oct_scale=oct_scale, coords=coords, map_coords=map_coords,
+                   subv_map_coords=subv_map_coords, voxel_val=voxel_val)
 
     def set_orientator_info(self, eqsp_size, radius):
-        self.eqsp_size = eqsp_size
-        self.box_size = radius * 2 + 1
-        self.box_side = radius
+        """mad/DensityFeature.py:43-52 without the per-feature patch / histogram scratch arrays."""
+        self._take(eqsp_size=eqsp_size)
+        self._patch_geometry(radius)
 
     def set_descriptor_info(self, subeqsp_size, radius):
-        self.subeqsp_size = subeqsp_size
-        self.box_size = radius * 2 + 1
-        self.box_side = radius
+        """mad/DensityFeature.py:54-57."""
+        self._take(subeqsp_size=subeqsp_size)
+        self._patch_geometry(radius)
+
+    def _from_file(self, index, main_bin, sec_bin, oct_scale, eqsp_size, coord, map_coord, subv_map_coord, Rfinal):
+        self._take(index=index, main_bin=main_bin, sec_bin=sec_bin, oct_scale=oct_scale, eqsp_size=eqsp_size,
+                   coords=coord, map_coords=map_coord, subv_map_coords=subv_map_coord, Rfinal=Rfinal)
 
     def set_from_file_ori(self, index, main_bin, sec_bin, oct_scale, eqsp_size,
                           coord, map_coord, subv_map_coord, Rfinal, ar_count):
-        self.set_detector_info(index, oct_scale, coord, map_coord, subv_map_coord, self.voxel_val)
-        self.eqsp_size = eqsp_size
-        self.main_bin = main_bin
-        self.sec_bin = sec_bin
-        self.Rfinal = Rfinal
-        self.ar_count = ar_count
+        """A cached oriented feature (mad/DensityFeature.py:59-70)."""
+        self._from_file(index, main_bin, sec_bin, oct_scale, eqsp_size, coord, map_coord, subv_map_coord, Rfinal)
+        self._take(ar_count=ar_count)
 
     def set_from_file_dsc(self, index, main_bin, sec_bin, oct_scale, eqsp_size, subeqsp_size,
                           coord, map_coord, subv_map_coord, Rfinal, descr):
-        self.set_detector_info(index, oct_scale, coord, map_coord, subv_map_coord, self.voxel_val)
-        self.eqsp_size = eqsp_size
-        self.subeqsp_size = subeqsp_size
-        self.main_bin = main_bin
-        self.sec_bin = sec_bin
-        self.Rfinal = Rfinal
-        self.lin_ar_subeqsp = descr
+        """A cached described feature (mad/DensityFeature.py:72-84; the descriptor cache of mad/MaD.py:857-875)."""
+        self._from_file(index, main_bin, sec_bin, oct_scale, eqsp_size, coord, map_coord, subv_map_coord, Rfinal)
+        self._take(subeqsp_size=subeqsp_size, lin_ar_subeqsp=descr)
 
     def show(self):
         print("DF @o=%i: idx=%i main_bin=%i sec_bin=%i (EQSP %i)" % (self.oct_scale, self.index, self.main_bin,

@@ -9,13 +9,12 @@ from .DensityFeature import DensityFeature, FeatureList
 
 
 class Detector(object):
+    # rejection statistics the reference keeps as attributes (mad/Detector.py:9-15; never read by MaD)
+    COUNTERS = ("lowdensity", "lowcontrast", "saddlepoint", "lowratio", "largeoffset", "badhessian")
+
     def __init__(self):
-        self.lowdensity = 0
-        self.lowcontrast = 0
-        self.saddlepoint = 0
-        self.lowratio = 0
-        self.largeoffset = 0
-        self.badhessian = 0
+        for name in self.COUNTERS:
+            setattr(self, name, 0)
 
     def find_anchors(self, ms, outname=""):
         if outname != "" and not os.path.exists(os.path.split(outname)[0]):
